@@ -1,0 +1,646 @@
+// capi.cu — implementation of the C ABI declared in include/tinympc_b200.h.
+//
+// Host glue only: handle management, problem upload, workspace sizing, kernel-family selection,
+// launch + CUDA-event timing, and the host-pointer convenience path (pinned staging, chunked so that
+// H2D copies, the solve kernel and D2H copies of consecutive chunks overlap on three streams).
+// No CPU fallback exists: every solve goes through a CUDA kernel of this library or returns an error.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "host_precompute.h"
+#include "launch.h"
+
+#define TM_DECL(nx, nu) extern "C" const tmpc::DimEntry *tm_dim_entry_##nx##_##nu();
+TM_DIMS(TM_DECL)
+#undef TM_DECL
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                             \
+    do {                                                                                           \
+        cudaError_t e_ = (expr);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(TINYMPC_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));     \
+    } while (0)
+
+const tmpc::DimEntry *find_dim(int nx, int nu) {
+#define TM_FIND(a, b) \
+    if (nx == a && nu == b) return tm_dim_entry_##a##_##b();
+    TM_DIMS(TM_FIND)
+#undef TM_FIND
+    return nullptr;
+}
+
+size_t esize(int dtype) { return dtype == TINYMPC_F64 ? 8 : 4; }
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t n) {
+        if (n <= bytes) return 0;
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+        if (cudaMalloc(&p, n) != cudaSuccess) return -1;
+        bytes = n;
+        return 0;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+};
+struct PinBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t n) {
+        if (n <= bytes) return 0;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        bytes = 0;
+        if (cudaMallocHost(&p, n) != cudaSuccess) return -1;
+        bytes = n;
+        return 0;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        bytes = 0;
+    }
+};
+
+std::vector<char> copy_bytes(const void *p, size_t n) {
+    std::vector<char> v(n);
+    if (n) std::memcpy(v.data(), p, n);
+    return v;
+}
+
+}  // namespace
+
+struct tinympc_b200_solver {
+    int device = 0;
+    int sm_count = 0;
+    int max_smem_optin = 0;
+    int nx = 0, nu = 0, N = 0, dtype = 0;
+    double rho = 0;
+    const tmpc::DimEntry *dim = nullptr;
+    // host copies (native dtype, column-major)
+    std::vector<char> A, Bm, f, Qd, Rd, Kinf, Pinf, Quu, AmBKt, APf, BPf;
+    bool has_xb = false, has_ub = false;
+    int ncx = 0, ncu = 0, nlx = 0, nlu = 0, ntvx = 0, ntvu = 0;
+    int cone_x_start[4] = {0, 0, 0, 0}, cone_u_start[4] = {0, 0, 0, 0};
+    double cone_x_mu[4] = {0, 0, 0, 0}, cone_u_mu[4] = {0, 0, 0, 0};
+    // device copies
+    DevBuf d_xmin, d_xmax, d_umin, d_umax, d_blob;
+    int bounds_tv = 0;
+    DevBuf d_Alin_x, d_blin_x, d_Alin_u, d_blin_u, d_tvA_x, d_tvb_x, d_tvA_u, d_tvb_u;
+    tinympc_settings_t settings;
+    int mode = TINYMPC_MODE_STRICT;
+    int family = TINYMPC_KERNEL_AUTO;
+    // workspace
+    DevBuf ws;
+    DevBuf queue;
+    // host-path staging (per pipeline slot)
+    static constexpr int SLOTS = 3;
+    DevBuf dio[SLOTS];
+    PinBuf pin_in[SLOTS], pin_out[SLOTS];
+    cudaStream_t st_h2d = nullptr, st_k = nullptr, st_d2h = nullptr;
+    cudaEvent_t ev_in[SLOTS] = {}, ev_k[SLOTS] = {}, ev_out[SLOTS] = {};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+    tinympc_b200_stats_t stats;
+};
+
+namespace {
+
+int upload(DevBuf &b, const void *src, size_t n) {
+    if (!src || n == 0) return 0;
+    if (b.ensure(n)) return -1;
+    return cudaMemcpy(b.p, src, n, cudaMemcpyHostToDevice) == cudaSuccess ? 0 : -1;
+}
+
+struct Features {
+    int soc_x, soc_u, lin_x, lin_u, tvl_x, tvl_u, ext;
+};
+Features features(const tinympc_b200_solver *s) {
+    Features f;
+    const tinympc_settings_t &st = s->settings;
+    f.soc_x = st.en_state_soc && s->ncx > 0;
+    f.soc_u = st.en_input_soc && s->ncu > 0;
+    f.lin_x = st.en_state_linear != 0;
+    f.lin_u = st.en_input_linear != 0;
+    f.tvl_x = st.en_tv_state_linear != 0;
+    f.tvl_u = st.en_tv_input_linear != 0;
+    f.ext = f.soc_x || f.soc_u || f.lin_x || f.lin_u || f.tvl_x || f.tvl_u;
+    return f;
+}
+
+int check_ready(const tinympc_b200_solver *s) {
+    const tinympc_settings_t &st = s->settings;
+    if ((st.en_state_bound && !s->has_xb) || (st.en_input_bound && !s->has_ub))
+        return fail(TINYMPC_ERR_NO_BOUNDS, "en_state_bound/en_input_bound set but bounds were never provided");
+    if (st.en_state_linear && s->nlx > 0 && !s->d_Alin_x.p) return fail(TINYMPC_ERR_ARG, "state linear constraints enabled but not set");
+    if (st.check_termination <= 0) return fail(TINYMPC_ERR_ARG, "check_termination must be >= 1");
+    return 0;
+}
+
+int resolve_family(const tinympc_b200_solver *s, const Features &ft, int *smem_out) {
+    int smem = 0;
+    bool gpi_ok = false;
+    if (!ft.ext && s->dim->gpi_fit) {
+        smem = s->dim->gpi_fit(s->dtype, s->N, s->max_smem_optin);
+        gpi_ok = smem > 0;
+    }
+    if (smem_out) *smem_out = smem;
+    if (s->family == TINYMPC_KERNEL_GPI) return gpi_ok ? TINYMPC_KERNEL_GPI : -1;
+    if (s->family == TINYMPC_KERNEL_TPI) return TINYMPC_KERNEL_TPI;
+    return gpi_ok ? TINYMPC_KERNEL_GPI : TINYMPC_KERNEL_TPI;
+}
+
+// carve the TPI structure-of-arrays workspace
+int setup_workspace(tinympc_b200_solver *s, tmpc::LaunchDesc &d, const Features &ft, int64_t B, int family) {
+    const int64_t Bpad = (B + 31) / 32 * 32;
+    d.Bpad = Bpad;
+    if (family != TINYMPC_KERNEL_TPI) return 0;
+    const int E = s->dtype == TINYMPC_F64 ? 2 : 4;
+    const size_t nxv = (s->nx + E - 1) / E, nuv = (s->nu + E - 1) / E;
+    const size_t szx = (size_t)s->N * nxv * 16 * Bpad, szu = (size_t)(s->N - 1) * nuv * 16 * Bpad;
+    size_t total = 3 * szx + 4 * szu;
+    if (ft.soc_x) total += 2 * szx;
+    if (ft.soc_u) total += 2 * szu;
+    if (ft.lin_x) total += 2 * szx;
+    if (ft.lin_u) total += 2 * szu;
+    if (ft.tvl_x) total += 2 * szx;
+    if (ft.tvl_u) total += 2 * szu;
+    if (s->ws.ensure(total + 256)) return fail(TINYMPC_ERR_CUDA, "workspace allocation failed");
+    char *c = (char *)s->ws.p;
+    auto take = [&](size_t n) {
+        void *r = c;
+        c += n;
+        return r;
+    };
+    d.w_v[0] = take(szx); d.w_v[1] = take(szx); d.w_g = take(szx);
+    d.w_z[0] = take(szu); d.w_z[1] = take(szu); d.w_y = take(szu); d.w_d = take(szu);
+    d.w_vc = d.w_gc = d.w_zc = d.w_yc = d.w_vl = d.w_gl = d.w_zl = d.w_yl = d.w_vlt = d.w_glt = d.w_zlt = d.w_ylt = nullptr;
+    if (ft.soc_x) { d.w_vc = take(szx); d.w_gc = take(szx); }
+    if (ft.soc_u) { d.w_zc = take(szu); d.w_yc = take(szu); }
+    if (ft.lin_x) { d.w_vl = take(szx); d.w_gl = take(szx); }
+    if (ft.lin_u) { d.w_zl = take(szu); d.w_yl = take(szu); }
+    if (ft.tvl_x) { d.w_vlt = take(szx); d.w_glt = take(szx); }
+    if (ft.tvl_u) { d.w_zlt = take(szu); d.w_ylt = take(szu); }
+    return 0;
+}
+
+void base_desc(const tinympc_b200_solver *s, tmpc::LaunchDesc &d, const Features &ft) {
+    std::memset(&d, 0, sizeof(d));
+    d.dtype = s->dtype;
+    d.fast = s->mode == TINYMPC_MODE_FAST;
+    d.ext = ft.ext;
+    d.A = s->A.data(); d.Bm = s->Bm.data(); d.f = s->f.data(); d.Qd = s->Qd.data(); d.Rd = s->Rd.data();
+    d.Kinf = s->Kinf.data(); d.Pinf = s->Pinf.data(); d.Quu = s->Quu.data(); d.AmBKt = s->AmBKt.data();
+    d.APf = s->APf.data(); d.BPf = s->BPf.data();
+    d.rho = s->rho;
+    const tinympc_settings_t &st = s->settings;
+    d.pri_tol = st.abs_pri_tol; d.dua_tol = st.abs_dua_tol;
+    d.N = s->N; d.max_iter = st.max_iter; d.check_termination = st.check_termination;
+    d.en_state_bound = st.en_state_bound; d.en_input_bound = st.en_input_bound;
+    d.soc_x = ft.soc_x; d.soc_u = ft.soc_u;
+    d.ncx = st.en_state_soc ? s->ncx : 0; d.ncu = st.en_input_soc ? s->ncu : 0;
+    d.lin_x = ft.lin_x; d.lin_u = ft.lin_u; d.nlx = s->nlx; d.nlu = s->nlu;
+    d.tvl_x = ft.tvl_x; d.tvl_u = ft.tvl_u; d.ntvx = s->ntvx; d.ntvu = s->ntvu;
+    for (int c = 0; c < 4; ++c) {
+        d.cone_x_start[c] = s->cone_x_start[c]; d.cone_u_start[c] = s->cone_u_start[c];
+        d.cone_x_mu[c] = s->cone_x_mu[c]; d.cone_u_mu[c] = s->cone_u_mu[c];
+    }
+    d.x_min = s->d_xmin.p; d.x_max = s->d_xmax.p; d.u_min = s->d_umin.p; d.u_max = s->d_umax.p;
+    d.Alin_x = s->d_Alin_x.p; d.blin_x = s->d_blin_x.p; d.Alin_u = s->d_Alin_u.p; d.blin_u = s->d_blin_u.p;
+    d.tv_Alin_x = s->d_tvA_x.p; d.tv_blin_x = s->d_tvb_x.p; d.tv_Alin_u = s->d_tvA_u.p; d.tv_blin_u = s->d_tvb_u.p;
+    d.gmat = s->d_blob.p;
+    d.bounds_tv = s->bounds_tv;
+    d.sm_count = s->sm_count;
+    d.max_smem_optin = s->max_smem_optin;
+}
+
+// enqueue one batched solve on `stream` (device pointers); fills stats
+int enqueue(tinympc_b200_solver *s, const tinympc_batch_t *io, cudaStream_t stream, bool timed) {
+    if (int rc = check_ready(s)) return rc;
+    if (!io->x0 || !io->Xref || !io->sol_x || !io->sol_u) return fail(TINYMPC_ERR_ARG, "x0, Xref, sol_x, sol_u are required");
+    if (io->B <= 0) return TINYMPC_OK;
+    const Features ft = features(s);
+    int smem = 0;
+    const int family = resolve_family(s, ft, &smem);
+    if (family < 0) return fail(TINYMPC_ERR_UNSUPPORTED, "GPI kernel requested but it does not support this problem (features or shared-memory footprint)");
+    tmpc::LaunchDesc d;
+    base_desc(s, d, ft);
+    d.family = family;
+    d.io = *io;
+    d.stream = stream;
+    if (int rc = setup_workspace(s, d, ft, io->B, family)) return rc;
+    if (family == TINYMPC_KERNEL_GPI) {
+        if (s->queue.ensure(256)) return fail(TINYMPC_ERR_CUDA, "queue allocation failed");
+        CUDA_TRY(cudaMemsetAsync(s->queue.p, 0, 256, stream));
+        d.work_queue = s->queue.p;
+    }
+    if (timed) CUDA_TRY(cudaEventRecord(s->ev0, stream));
+    int rc = s->dim->launch(&d);
+    if (rc == TINYMPC_ERR_CUDA) return fail(rc, std::string("kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+    if (rc) return fail(rc, "no compiled kernel for this (dtype, mode, family) combination");
+    if (timed) CUDA_TRY(cudaEventRecord(s->ev1, stream));
+    s->timed = timed;
+    s->stats.instances = io->B;
+    s->stats.kernel_launches = 1;
+    s->stats.kernel_family = family;
+    s->stats.lanes_per_instance = d.out_lanes_per_instance;
+    s->stats.instances_per_cta = d.out_instances_per_cta;
+    s->stats.smem_bytes_per_cta = d.out_smem;
+    s->stats.ctas = d.out_ctas;
+    s->stats.threads_per_cta = d.out_threads;
+    return TINYMPC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *tinympc_b200_last_error(void) { return g_err.c_str(); }
+const char *tinympc_b200_version(void) { return "tinympc_b200 0.1 (sm_100a)"; }
+
+int tinympc_b200_supported(int32_t dtype, int32_t nx, int32_t nu) {
+    return (dtype == TINYMPC_F32 || dtype == TINYMPC_F64) && find_dim(nx, nu) != nullptr;
+}
+
+int tinympc_b200_default_settings(tinympc_settings_t *s) {
+    if (!s) return fail(TINYMPC_ERR_ARG, "settings is null");
+    s->abs_pri_tol = 1e-3;  // tiny_api_constants.hpp:5-16
+    s->abs_dua_tol = 1e-3;
+    s->max_iter = 1000;
+    s->check_termination = 1;
+    s->en_state_bound = 1;
+    s->en_input_bound = 1;
+    s->en_state_soc = 0;
+    s->en_input_soc = 0;
+    s->en_state_linear = 0;
+    s->en_input_linear = 0;
+    s->en_tv_state_linear = 0;
+    s->en_tv_input_linear = 0;
+    return TINYMPC_OK;
+}
+
+int tinympc_b200_precompute_cache(int32_t dtype, int32_t nx, int32_t nu, double rho, const void *A, const void *B,
+                                  const void *f, const void *Q, const void *R, void *Kinf, void *Pinf, void *Quu_inv,
+                                  void *AmBKt, void *APf, void *BPf) {
+    if (!A || !B || !f || !Q || !R || !Kinf || !Pinf || !Quu_inv || !AmBKt || !APf || !BPf || nx <= 0 || nu <= 0)
+        return fail(TINYMPC_ERR_ARG, "null pointer or bad size");
+    int rc;
+    if (dtype == TINYMPC_F64)
+        rc = tmpc::precompute_cache<double>(nx, nu, rho, (const double *)A, (const double *)B, (const double *)f,
+                                            (const double *)Q, (const double *)R, (double *)Kinf, (double *)Pinf,
+                                            (double *)Quu_inv, (double *)AmBKt, (double *)APf, (double *)BPf);
+    else if (dtype == TINYMPC_F32)
+        rc = tmpc::precompute_cache<float>(nx, nu, rho, (const float *)A, (const float *)B, (const float *)f,
+                                           (const float *)Q, (const float *)R, (float *)Kinf, (float *)Pinf,
+                                           (float *)Quu_inv, (float *)AmBKt, (float *)APf, (float *)BPf);
+    else
+        return fail(TINYMPC_ERR_ARG, "bad dtype");
+    if (rc < 0) return fail(TINYMPC_ERR_ARG, "singular R + B'PB in the Riccati recursion");
+    return rc;
+}
+
+int tinympc_b200_create(const tinympc_problem_t *p, int32_t device, tinympc_b200_solver_t **out) {
+    if (!p || !out) return fail(TINYMPC_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (p->nx <= 0 || p->nu <= 0 || p->N < 2) return fail(TINYMPC_ERR_ARG, "need nx>0, nu>0, N>=2");
+    if (p->dtype != TINYMPC_F32 && p->dtype != TINYMPC_F64) return fail(TINYMPC_ERR_ARG, "bad dtype");
+    if (!p->Adyn || !p->Bdyn || !p->fdyn || !p->Q || !p->R || !p->Kinf || !p->Pinf || !p->Quu_inv || !p->AmBKt ||
+        !p->APf || !p->BPf)
+        return fail(TINYMPC_ERR_ARG, "model / cache pointer is null");
+    const tmpc::DimEntry *dim = find_dim(p->nx, p->nu);
+    if (!dim) return fail(TINYMPC_ERR_UNSUPPORTED, "no kernel compiled for this (nx, nu); add it to TM_DIMS in csrc/launch.h");
+    if (p->num_state_cones > 4 || p->num_input_cones > 4) return fail(TINYMPC_ERR_UNSUPPORTED, "at most 4 cones per side");
+    for (int c = 0; c < p->num_state_cones; ++c)
+        if (p->qcx[c] != 3 || p->Acx[c] < 0 || p->Acx[c] + 3 > p->nx) return fail(TINYMPC_ERR_CONE_DIM, "state cone must be 3-dimensional and inside the state");
+    for (int c = 0; c < p->num_input_cones; ++c)
+        if (p->qcu[c] != 3 || p->Acu[c] < 0 || p->Acu[c] + 3 > p->nu) return fail(TINYMPC_ERR_CONE_DIM, "input cone must be 3-dimensional and inside the input");
+
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(TINYMPC_ERR_ARG, "bad device index");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(TINYMPC_ERR_UNSUPPORTED, "this library is built for sm_100a (B200) only");
+
+    tinympc_b200_solver *s = new tinympc_b200_solver();
+    s->device = device;
+    s->sm_count = prop.multiProcessorCount;
+    s->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    s->nx = p->nx; s->nu = p->nu; s->N = p->N; s->dtype = p->dtype; s->rho = p->rho;
+    s->dim = dim;
+    const size_t es = esize(p->dtype), nx = p->nx, nu = p->nu, N = p->N;
+    s->A = copy_bytes(p->Adyn, es * nx * nx); s->Bm = copy_bytes(p->Bdyn, es * nx * nu); s->f = copy_bytes(p->fdyn, es * nx);
+    s->Qd = copy_bytes(p->Q, es * nx); s->Rd = copy_bytes(p->R, es * nu);
+    s->Kinf = copy_bytes(p->Kinf, es * nu * nx); s->Pinf = copy_bytes(p->Pinf, es * nx * nx);
+    s->Quu = copy_bytes(p->Quu_inv, es * nu * nu); s->AmBKt = copy_bytes(p->AmBKt, es * nx * nx);
+    s->APf = copy_bytes(p->APf, es * nx); s->BPf = copy_bytes(p->BPf, es * nu);
+    tinympc_b200_default_settings(&s->settings);
+    bool ok = true;
+    {   // packed cache blob for the GPI kernel's TMA staging: A,B,f,Qd,Rd,Kinf,Pinf,Quu,AmBKt,APf,BPf
+        std::vector<char> blob;
+        for (const std::vector<char> *v : {&s->A, &s->Bm, &s->f, &s->Qd, &s->Rd, &s->Kinf, &s->Pinf, &s->Quu, &s->AmBKt, &s->APf, &s->BPf})
+            blob.insert(blob.end(), v->begin(), v->end());
+        blob.resize((blob.size() + 63) / 64 * 64, 0);
+        ok &= !upload(s->d_blob, blob.data(), blob.size());
+    }
+    auto varies = [&](const void *m, size_t rows, size_t cols) {  // does a (rows x cols) column-major matrix vary along columns?
+        if (!m) return false;
+        const char *c = (const char *)m;
+        for (size_t k = 1; k < cols; ++k)
+            if (std::memcmp(c, c + k * rows * es, rows * es) != 0) return true;
+        return false;
+    };
+    s->bounds_tv = varies(p->x_min, nx, N) || varies(p->x_max, nx, N) || varies(p->u_min, nu, N - 1) || varies(p->u_max, nu, N - 1);
+    if (p->x_min && p->x_max) {
+        ok &= !upload(s->d_xmin, p->x_min, es * nx * N) && !upload(s->d_xmax, p->x_max, es * nx * N);
+        s->has_xb = true;
+    }
+    if (p->u_min && p->u_max) {
+        ok &= !upload(s->d_umin, p->u_min, es * nu * (N - 1)) && !upload(s->d_umax, p->u_max, es * nu * (N - 1));
+        s->has_ub = true;
+    }
+    auto rd = [&](const void *base, int i) { return p->dtype == TINYMPC_F64 ? ((const double *)base)[i] : (double)((const float *)base)[i]; };
+    s->ncx = p->num_state_cones; s->ncu = p->num_input_cones;
+    for (int c = 0; c < s->ncx; ++c) { s->cone_x_start[c] = p->Acx[c]; s->cone_x_mu[c] = rd(p->cx, c); }
+    for (int c = 0; c < s->ncu; ++c) { s->cone_u_start[c] = p->Acu[c]; s->cone_u_mu[c] = rd(p->cu, c); }
+    s->nlx = p->num_state_linear; s->nlu = p->num_input_linear;
+    if (s->nlx > 0) ok &= !upload(s->d_Alin_x, p->Alin_x, es * s->nlx * nx) && !upload(s->d_blin_x, p->blin_x, es * s->nlx);
+    if (s->nlu > 0) ok &= !upload(s->d_Alin_u, p->Alin_u, es * s->nlu * nu) && !upload(s->d_blin_u, p->blin_u, es * s->nlu);
+    s->ntvx = p->num_tv_state_linear; s->ntvu = p->num_tv_input_linear;
+    if (s->ntvx > 0) ok &= !upload(s->d_tvA_x, p->tv_Alin_x, es * s->ntvx * N * nx) && !upload(s->d_tvb_x, p->tv_blin_x, es * s->ntvx * N);
+    if (s->ntvu > 0) ok &= !upload(s->d_tvA_u, p->tv_Alin_u, es * s->ntvu * (N - 1) * nu) && !upload(s->d_tvb_u, p->tv_blin_u, es * s->ntvu * (N - 1));
+    ok &= cudaEventCreate(&s->ev0) == cudaSuccess && cudaEventCreate(&s->ev1) == cudaSuccess;
+    if (!ok) {
+        tinympc_b200_destroy(s);
+        return fail(TINYMPC_ERR_CUDA, std::string("problem upload failed: ") + cudaGetErrorString(cudaGetLastError()));
+    }
+    std::memset(&s->stats, 0, sizeof(s->stats));
+    *out = s;
+    return TINYMPC_OK;
+}
+
+int tinympc_b200_destroy(tinympc_b200_solver_t *s) {
+    if (!s) return TINYMPC_OK;
+    cudaSetDevice(s->device);
+    DevBuf *bufs[] = {&s->d_xmin, &s->d_xmax, &s->d_umin, &s->d_umax, &s->d_Alin_x, &s->d_blin_x, &s->d_Alin_u,
+                      &s->d_blin_u, &s->d_tvA_x, &s->d_tvb_x, &s->d_tvA_u, &s->d_tvb_u, &s->ws, &s->queue, &s->d_blob};
+    for (DevBuf *b : bufs) b->release();
+    for (int i = 0; i < tinympc_b200_solver::SLOTS; ++i) {
+        s->dio[i].release();
+        s->pin_in[i].release();
+        s->pin_out[i].release();
+        if (s->ev_in[i]) cudaEventDestroy(s->ev_in[i]);
+        if (s->ev_k[i]) cudaEventDestroy(s->ev_k[i]);
+        if (s->ev_out[i]) cudaEventDestroy(s->ev_out[i]);
+    }
+    if (s->st_h2d) cudaStreamDestroy(s->st_h2d);
+    if (s->st_k) cudaStreamDestroy(s->st_k);
+    if (s->st_d2h) cudaStreamDestroy(s->st_d2h);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    delete s;
+    return TINYMPC_OK;
+}
+
+int tinympc_b200_update_settings(tinympc_b200_solver_t *s, const tinympc_settings_t *st) {
+    if (!s || !st) return fail(TINYMPC_ERR_ARG, "null argument");
+    if (st->check_termination <= 0) return fail(TINYMPC_ERR_ARG, "check_termination must be >= 1");
+    s->settings = *st;
+    return TINYMPC_OK;
+}
+
+int tinympc_b200_get_settings(const tinympc_b200_solver_t *s, tinympc_settings_t *st) {
+    if (!s || !st) return fail(TINYMPC_ERR_ARG, "null argument");
+    *st = s->settings;
+    return TINYMPC_OK;
+}
+
+int tinympc_b200_set_mode(tinympc_b200_solver_t *s, int32_t mode, int32_t family) {
+    if (!s) return fail(TINYMPC_ERR_ARG, "null solver");
+    if (mode != TINYMPC_MODE_STRICT && mode != TINYMPC_MODE_FAST) return fail(TINYMPC_ERR_ARG, "bad mode");
+    if (family < TINYMPC_KERNEL_AUTO || family > TINYMPC_KERNEL_GPI) return fail(TINYMPC_ERR_ARG, "bad kernel family");
+    s->mode = mode;
+    s->family = family;
+    return TINYMPC_OK;
+}
+
+int tinympc_b200_solve(tinympc_b200_solver_t *s, const tinympc_batch_t *io, void *cuda_stream) {
+    if (!s || !io) return fail(TINYMPC_ERR_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(s->device));
+    return enqueue(s, io, (cudaStream_t)cuda_stream, true);
+}
+
+int tinympc_b200_get_stats(const tinympc_b200_solver_t *s, tinympc_b200_stats_t *out) {
+    if (!s || !out) return fail(TINYMPC_ERR_ARG, "null argument");
+    tinympc_b200_solver *m = const_cast<tinympc_b200_solver *>(s);
+    if (m->timed) {
+        CUDA_TRY(cudaSetDevice(s->device));
+        CUDA_TRY(cudaEventSynchronize(m->ev1));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, m->ev0, m->ev1));
+        m->stats.kernel_ms = ms;
+        m->timed = false;
+    }
+    *out = m->stats;
+    return TINYMPC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Host-pointer path.  The batch is cut into chunks; chunk c uses slot c % SLOTS (its own pinned in/out
+// buffers and device io buffers).  Three streams: H2D, kernels, D2H, chained by events, so that the copy
+// of chunk c+1 overlaps the solve of chunk c and the read-back of chunk c-1.
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+
+struct Field {
+    const void *src;   // host input (may be null)
+    void *dst;         // host output (may be null)
+    size_t per_inst;   // bytes per instance
+    bool is_in, is_out;
+    void **dev_slot;   // where the device pointer goes in the device-side tinympc_batch_t
+};
+
+}  // namespace
+
+int tinympc_b200_solve_host(tinympc_b200_solver_t *s, const tinympc_batch_t *io) {
+    if (!s || !io) return fail(TINYMPC_ERR_ARG, "null argument");
+    if (!io->x0 || !io->Xref || !io->sol_x || !io->sol_u) return fail(TINYMPC_ERR_ARG, "x0, Xref, sol_x, sol_u are required");
+    CUDA_TRY(cudaSetDevice(s->device));
+    if (int rc = check_ready(s)) return rc;
+    const int64_t B = io->B;
+    if (B <= 0) return TINYMPC_OK;
+    const size_t es = esize(s->dtype);
+    const size_t bx = es * s->nx * s->N, bu = es * s->nu * (s->N - 1);
+    constexpr int SLOTS = tinympc_b200_solver::SLOTS;
+    if (!s->st_h2d) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&s->st_h2d, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&s->st_k, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&s->st_d2h, cudaStreamNonBlocking));
+        for (int i = 0; i < SLOTS; ++i) {
+            CUDA_TRY(cudaEventCreateWithFlags(&s->ev_in[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&s->ev_k[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&s->ev_out[i], cudaEventDisableTiming));
+        }
+    }
+
+    // shared (not per-instance) references are uploaded once
+    DevBuf shared_ref;
+    tinympc_batch_t dev = *io;  // template for the device-side descriptor
+    const bool cold = io->cold_start != 0;
+    std::vector<Field> fields;
+    fields.push_back({io->x0, nullptr, es * s->nx, true, false, (void **)&dev.x0});
+    if (io->xref_per_instance) fields.push_back({io->Xref, nullptr, bx, true, false, (void **)&dev.Xref});
+    if (io->Uref && io->uref_per_instance) fields.push_back({io->Uref, nullptr, bu, true, false, (void **)&dev.Uref});
+    {
+        size_t need = (io->xref_per_instance ? 0 : bx) + ((io->Uref && !io->uref_per_instance) ? bu : 0);
+        if (need) {
+            if (shared_ref.ensure(need + 256)) return fail(TINYMPC_ERR_CUDA, "shared reference allocation failed");
+            char *c = (char *)shared_ref.p;
+            if (!io->xref_per_instance) {
+                CUDA_TRY(cudaMemcpyAsync(c, io->Xref, bx, cudaMemcpyHostToDevice, s->st_h2d));
+                dev.Xref = c;
+                c += (bx + 255) / 256 * 256;
+            }
+            if (io->Uref && !io->uref_per_instance) {
+                CUDA_TRY(cudaMemcpyAsync(c, io->Uref, bu, cudaMemcpyHostToDevice, s->st_h2d));
+                dev.Uref = c;
+            }
+        }
+    }
+    {
+        void *const *sp = (void *const *)&io->state;
+        void **dp = (void **)&dev.state;
+        const int nfields = sizeof(tinympc_state_t) / sizeof(void *);
+        for (int i = 0; i < nfields; ++i) {
+            if (!sp[i]) continue;
+            const bool is_x = (i % 2) == 0;  // x,v,vnew,g,... alternate with u,z,znew,y,...
+            fields.push_back({cold ? nullptr : sp[i], sp[i], is_x ? bx : bu, !cold, true, &dp[i]});
+        }
+    }
+    fields.push_back({nullptr, io->sol_x, bx, false, true, (void **)&dev.sol_x});
+    fields.push_back({nullptr, io->sol_u, bu, false, true, (void **)&dev.sol_u});
+    if (io->iter) fields.push_back({nullptr, io->iter, sizeof(int32_t), false, true, (void **)&dev.iter});
+    if (io->solved) fields.push_back({nullptr, io->solved, sizeof(int32_t), false, true, (void **)&dev.solved});
+    if (io->residuals) fields.push_back({nullptr, io->residuals, 4 * es, false, true, (void **)&dev.residuals});
+
+    size_t per_inst_dev = 0, per_inst_in = 0, per_inst_out = 0;
+    for (const Field &f : fields) {
+        per_inst_dev += f.per_inst;
+        if (f.is_in) per_inst_in += f.per_inst;
+        if (f.is_out) per_inst_out += f.per_inst;
+    }
+    // chunking: big enough to fill the GPU several times over, small enough to pipeline
+    int64_t chunk = B;
+    if (B > 16384) chunk = std::max<int64_t>(8192, (B + 7) / 8);
+    chunk = (chunk + 31) / 32 * 32;
+    const int64_t nchunks = (B + chunk - 1) / chunk;
+    const size_t align = 256;
+    auto padded = [&](size_t n) { return (n + align - 1) / align * align; };
+    size_t dev_bytes = 0, in_bytes = 0, out_bytes = 0;
+    for (const Field &f : fields) {
+        dev_bytes += padded(f.per_inst * chunk);
+        if (f.is_in) in_bytes += padded(f.per_inst * chunk);
+        if (f.is_out) out_bytes += padded(f.per_inst * chunk);
+    }
+    const int used_slots = (int)std::min<int64_t>(SLOTS, nchunks);
+    for (int i = 0; i < used_slots; ++i) {
+        if (s->dio[i].ensure(dev_bytes) || s->pin_in[i].ensure(in_bytes + align) || s->pin_out[i].ensure(out_bytes + align))
+            return fail(TINYMPC_ERR_CUDA, "staging allocation failed");
+    }
+    int64_t launches = 0;
+    struct Pending { int64_t b0, nb; bool active; };
+    Pending pend[SLOTS] = {};
+    auto drain = [&](int slot) -> int {  // copy the pinned outputs of a finished chunk to the user's buffers
+        if (!pend[slot].active) return 0;
+        if (cudaEventSynchronize(s->ev_out[slot]) != cudaSuccess) return -1;
+        char *po = (char *)s->pin_out[slot].p;
+        for (const Field &f : fields) {
+            if (!f.is_out) continue;
+            std::memcpy((char *)f.dst + f.per_inst * pend[slot].b0, po, f.per_inst * pend[slot].nb);
+            po += padded(f.per_inst * chunk);
+        }
+        pend[slot].active = false;
+        return 0;
+    };
+    for (int64_t c = 0; c < nchunks; ++c) {
+        const int slot = (int)(c % SLOTS);
+        const int64_t b0 = c * chunk, nb = std::min<int64_t>(chunk, B - b0);
+        if (drain(slot)) return fail(TINYMPC_ERR_CUDA, "event sync failed");
+        // stage inputs into pinned memory, then one async copy per field
+        char *pi = (char *)s->pin_in[slot].p, *pd = (char *)s->dio[slot].p;
+        tinympc_batch_t d = dev;
+        d.B = nb;
+        // device layout
+        {
+            char *cur = pd;
+            const char *base = (const char *)&dev;
+            for (const Field &f : fields) {
+                size_t off = (const char *)f.dev_slot - base;
+                *(void **)((char *)&d + off) = cur;
+                cur += padded(f.per_inst * chunk);
+            }
+        }
+        {
+            char *cur = pd;
+            for (const Field &f : fields) {
+                if (f.is_in && f.src) {
+                    std::memcpy(pi, (const char *)f.src + f.per_inst * b0, f.per_inst * nb);
+                    CUDA_TRY(cudaMemcpyAsync(cur, pi, f.per_inst * nb, cudaMemcpyHostToDevice, s->st_h2d));
+                    pi += padded(f.per_inst * chunk);
+                }
+                cur += padded(f.per_inst * chunk);
+            }
+        }
+        CUDA_TRY(cudaEventRecord(s->ev_in[slot], s->st_h2d));
+        CUDA_TRY(cudaStreamWaitEvent(s->st_k, s->ev_in[slot], 0));
+        if (int rc = enqueue(s, &d, s->st_k, false)) return rc;
+        ++launches;
+        CUDA_TRY(cudaEventRecord(s->ev_k[slot], s->st_k));
+        CUDA_TRY(cudaStreamWaitEvent(s->st_d2h, s->ev_k[slot], 0));
+        {
+            char *cur = pd, *po = (char *)s->pin_out[slot].p;
+            for (const Field &f : fields) {
+                if (f.is_out) {
+                    CUDA_TRY(cudaMemcpyAsync(po, cur, f.per_inst * nb, cudaMemcpyDeviceToHost, s->st_d2h));
+                    po += padded(f.per_inst * chunk);
+                }
+                cur += padded(f.per_inst * chunk);
+            }
+        }
+        CUDA_TRY(cudaEventRecord(s->ev_out[slot], s->st_d2h));
+        // the next use of this slot's pinned input buffer must wait for its H2D copy: ev_in is synchronised
+        // implicitly because drain() waits for ev_out, which is ordered after ev_in.
+        pend[slot] = {b0, nb, true};
+    }
+    for (int i = 0; i < SLOTS; ++i)
+        if (drain(i)) return fail(TINYMPC_ERR_CUDA, "event sync failed");
+    CUDA_TRY(cudaStreamSynchronize(s->st_h2d));
+    shared_ref.release();
+    s->stats.instances = B;
+    s->stats.kernel_launches = launches;
+    s->timed = false;
+    s->stats.kernel_ms = 0.f;
+    (void)per_inst_dev; (void)per_inst_in; (void)per_inst_out;
+    return TINYMPC_OK;
+}
+
+}  // extern "C"

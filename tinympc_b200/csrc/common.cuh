@@ -1,0 +1,123 @@
+// common.cuh — arithmetic policy + kernel parameter block shared by the TPI and GPI kernels.
+//
+// Arithmetic contract:
+//   every translation unit is compiled with -fmad=false, so plain `a*b + c` is NEVER contracted;
+//   STRICT mode uses plain operators only  -> bit-identical to the pinned reference build
+//   FAST   mode calls fma()/fmaf() explicitly in dot products and axpy-like updates (same order of terms).
+// Division and square root are IEEE (no --use_fast_math).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tmpc {
+
+template <bool FAST, typename T>
+__device__ __forceinline__ T mac(T acc, T a, T b) {  // acc + a*b
+    if constexpr (FAST) {
+        return fma(a, b, acc);
+    } else {
+        return acc + a * b;
+    }
+}
+template <bool FAST, typename T>
+__device__ __forceinline__ T nmac(T acc, T a, T b) {  // acc - a*b
+    if constexpr (FAST) {
+        return fma(-a, b, acc);
+    } else {
+        return acc - a * b;
+    }
+}
+template <typename T>
+__device__ __forceinline__ T tabs(T a) {
+    return a < T(0) ? -a : a;
+}
+__device__ __forceinline__ float tabs(float a) { return fabsf(a); }
+__device__ __forceinline__ double tabs(double a) { return fabs(a); }
+__device__ __forceinline__ float tsqrt(float a) { return sqrtf(a); }
+__device__ __forceinline__ double tsqrt(double a) { return sqrt(a); }
+
+// Eigen's x_max.cwiseMin(x_min.cwiseMax(v)) as executed: m = (lo<v)?v:lo ; r = (m<hi)?m:hi
+template <typename T>
+__device__ __forceinline__ T clamp_ref(T v, T lo, T hi) {
+    T m = (lo < v) ? v : lo;
+    return (m < hi) ? m : hi;
+}
+
+// project_soc for a 3-vector exactly as the reference executes it (admm.cpp:39-60):
+// mu and the norm are narrowed to float even when T = double.
+template <typename T>
+__device__ __forceinline__ void project_soc3(T &s0, T &s1, T &s2, T mu_T) {
+    const float mu = (float)mu_T;
+    const T u0 = s2 * (T)mu;
+    T sq = s0 * s0;
+    sq = sq + s1 * s1;
+    const float a = (float)tsqrt(sq);
+    if ((T)a <= -u0) {
+        s0 = T(0);
+        s1 = T(0);
+        s2 = T(0);
+    } else if ((T)a <= u0) {
+        // inside the cone: unchanged
+    } else {
+        const T third = (T)(a / mu);  // float division (admm.cpp:54)
+        const T c = T(0.5) * (T(1) + u0 / (T)a);
+        s0 = c * s0;
+        s1 = c * s1;
+        s2 = c * third;
+    }
+}
+
+constexpr int MAX_CONES = 4;  // cones per knot point and per side held in the parameter block
+
+// Kernel parameter block.  Passed by value (__grid_constant__): it lives in the constant bank, so with
+// compile-time indices the matrix entries become immediate constant operands of the FMA instructions.
+// All matrices are column-major copies of the reference's cache / workspace (types.hpp:43-51,186-190).
+template <typename T, int NX, int NU>
+struct KParams {
+    T A[NX * NX];
+    T Bm[NX * NU];
+    T f[NX];
+    T Qd[NX];
+    T Rd[NU];
+    T Kinf[NU * NX];
+    T Pinf[NX * NX];
+    T Quu[NU * NU];
+    T AmBKt[NX * NX];
+    T APf[NX];
+    T BPf[NU];
+    T rho, pri_tol, dua_tol;
+    int N, max_iter, check_termination;
+    int en_state_bound, en_input_bound;
+    int soc_x, soc_u;    // en_*_soc && num cones > 0  (admm.cpp:102,107)
+    int ncx, ncu;        // cone loops run under en_*_soc alone (admm.cpp:112,125)
+    int lin_x, lin_u, nlx, nlu;
+    int tvl_x, tvl_u, ntvx, ntvu;
+    int cone_x_start[MAX_CONES], cone_u_start[MAX_CONES];
+    T cone_x_mu[MAX_CONES], cone_u_mu[MAX_CONES];
+    int64_t B;     // instances in this launch
+    int64_t Bpad;  // workspace stride (instances, multiple of 32)
+    int cold;
+    int bounds_tv;      // bounds vary along the horizon (else row 0 is used for every k)
+    const T *Pinf_g;    // Pinf in global memory (column-major), GPI terminal cost
+    int xref_pi, uref_pi;
+    // inputs (user layout, instance-major)
+    const T *x0, *Xref, *Uref;
+    // bounds (device, column-major nx x N etc.)
+    const T *x_min, *x_max, *u_min, *u_max;
+    // hyperplanes (device)
+    const T *Alin_x, *blin_x, *Alin_u, *blin_u;
+    const T *tv_Alin_x, *tv_blin_x, *tv_Alin_u, *tv_blin_u;
+    // warm-start state in/out (user layout), any may be null
+    T *s_x, *s_u, *s_v, *s_z, *s_vnew, *s_znew, *s_g, *s_y;
+    T *s_vcnew, *s_zcnew, *s_gc, *s_yc, *s_vlnew, *s_zlnew, *s_gl, *s_yl;
+    T *s_vlnew_tv, *s_zlnew_tv, *s_gl_tv, *s_yl_tv;
+    // outputs
+    T *sol_x, *sol_u;
+    int32_t *iter, *solved;
+    T *residuals;
+    // TPI workspace (structure-of-arrays, 16-byte vectors, [k][vec][Bpad])
+    void *w_v[2], *w_z[2], *w_g, *w_y, *w_d;
+    void *w_vc, *w_zc, *w_gc, *w_yc, *w_vl, *w_zl, *w_gl, *w_yl, *w_vlt, *w_zlt, *w_glt, *w_ylt;
+};
+
+}  // namespace tmpc

@@ -1,0 +1,581 @@
+// gpi_kernel.cuh — lane-group-per-instance (GPI) batched ADMM solve with the whole per-instance state
+// resident in shared memory.  This is the kernel BASELINE.json's north_star describes.
+//
+//   * L lanes (4, 8 or 16) own one MPC instance, 32/L instances per warp; lane l owns the state rows
+//     [l*RX, (l+1)*RX) and the input rows [l*RU, (l+1)*RU)  (RX = ceil(nx/L), RU = ceil(nu/L)) of every vector.
+//   * the rows of Kinf / Quu_inv / AmBKt / A / B that a lane needs are loaded ONCE into registers (staged
+//     through shared memory by a TMA bulk copy, cp.async.bulk), the p / x recursions run in registers, each
+//     mat-vec is RX (or RU) independent ascending-k dot products per lane (bit-identical to the pinned
+//     oracle in STRICT mode), and the freshly computed vector is all-gathered inside the lane group with
+//     warp shuffles;
+//   * the N-indexed state (vnew, g, znew, y, d) lives in shared memory for the whole solve, laid out
+//     [k][row slot][lane] so that every access of a warp is bank-conflict free; only the final
+//     trajectories / residuals are written back, through a coalescing transpose;
+//   * the kernel is persistent: one CTA per SM, every warp pulls the next group of 32/L instances from
+//     a global atomic counter until the batch is exhausted.
+// Reference semantics: tiny_solve -> solve (admm.cpp:331-455); per-iteration order as in SURVEY A.2.
+// Scope: box constraints (admm.cpp:85-98).  Cones / hyperplanes run on the TPI kernel.
+#pragma once
+#include <cuda/barrier>
+
+#include "common.cuh"
+#include "launch.h"
+
+namespace tmpc {
+
+template <int NX, int NU, int L>
+struct GpiCfg {
+    static constexpr int RX = (NX + L - 1) / L;
+    static constexpr int RU = (NU + L - 1) / L;
+    static constexpr int IPW = 32 / L;  // instances per warp
+    // registers needed for the per-lane matrix rows (in elements of T)
+    static constexpr int MAT_REGS = RX * (2 * NX + 2 * NU + 3) + RU * (2 * NX + NU + 2);
+    // shared-memory words (elements of T) per warp for horizon N
+    __host__ __device__ static constexpr size_t warp_elems(int N) { return (size_t)32 * ((size_t)N * RX * 2 + (size_t)(N - 1) * RU * 3); }
+};
+
+template <typename T, int NX, int NU, int L>
+constexpr bool gpi_feasible() {
+    // keep the matrix rows + working set under the 255-register ceiling
+    return GpiCfg<NX, NU, L>::MAT_REGS * (int)(sizeof(T) / 4) <= 150;
+}
+
+// all-gather of R values per lane inside an L-lane group -> full[j*R + a] = value a of lane j (absolute
+// lane order, so that dot products run over ascending column index as the oracle does)
+template <typename T, int R, int L, int NE>
+__device__ __forceinline__ void gather(const T (&own)[R], T (&full)[NE]) {
+#pragma unroll
+    for (int j = 0; j < L; ++j)
+#pragma unroll
+        for (int a = 0; a < R; ++a)
+            if (j * R + a < NE) full[j * R + a] = __shfl_sync(0xffffffffu, own[a], j, L);
+}
+
+template <typename T, int L>
+__device__ __forceinline__ T group_max(T v) {
+#pragma unroll
+    for (int m = L / 2; m >= 1; m >>= 1) {
+        T o = __shfl_xor_sync(0xffffffffu, v, m, L);
+        v = (o > v) ? o : v;
+    }
+    return v;
+}
+
+constexpr int GPI_MAX_WARPS = 8;
+
+template <typename T, int NX, int NU, int L, bool FAST>
+__global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
+    gpi_solve_kernel(const __grid_constant__ KParams<T, NX, NU> P, const T *__restrict__ gmat, unsigned long long *queue) {
+    using Cfg = GpiCfg<NX, NU, L>;
+    constexpr int RX = Cfg::RX, RU = Cfg::RU, IPW = Cfg::IPW;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int N = P.N;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int l = lane % L;         // lane inside the instance group
+    const int slot = lane / L;      // which of the warp's instances
+    const T rho = P.rho;
+
+    // ---- stage the cache blob (A, B, f, Qd, Rd, Kinf, Pinf, Quu, AmBKt, APf, BPf) into shared memory with
+    // one TMA bulk copy per CTA, then pull this lane's rows into registers.  The staging area aliases the
+    // first warp's state region and is dead before the solve starts.
+    constexpr int OFF_A = 0, OFF_B = OFF_A + NX * NX, OFF_F = OFF_B + NX * NU, OFF_QD = OFF_F + NX, OFF_RD = OFF_QD + NX,
+                  OFF_K = OFF_RD + NU, OFF_PINF = OFF_K + NU * NX, OFF_QUU = OFF_PINF + NX * NX,
+                  OFF_AMBKT = OFF_QUU + NU * NU, OFF_APF = OFF_AMBKT + NX * NX, OFF_BPF = OFF_APF + NX,
+                  BLOB = OFF_BPF + NU;
+    constexpr unsigned BLOB_BYTES = (unsigned)(((BLOB * sizeof(T) + 15) / 16) * 16);
+    T *stage = reinterpret_cast<T *>(smem_raw);
+    __shared__ __align__(8) unsigned long long mbar;
+    if (threadIdx.x == 0) {
+        const unsigned mb = (unsigned)__cvta_generic_to_shared(&mbar);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(BLOB_BYTES) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         (unsigned)__cvta_generic_to_shared(stage)),
+                     "l"(gmat), "r"(BLOB_BYTES), "r"(mb)
+                     : "memory");
+    }
+    __syncthreads();
+    {
+        const unsigned mb = (unsigned)__cvta_generic_to_shared(&mbar);
+        unsigned done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}\n"
+                : "=r"(done)
+                : "r"(mb)
+                : "memory");
+        }
+    }
+
+    // per-lane matrix rows (registers)
+    T mAmBKt[RX][NX], mKt[RX][NU], mA[RX][NX], mB[RX][NU], vQd[RX], vAPf[RX], vf[RX];
+    T mBt[RU][NX], mQuu[RU][NU], mK[RU][NX], vRd[RU], vBPf[RU];
+    bool xv[RX], uv[RU];  // row validity (padding rows compute zeros and never store)
+#pragma unroll
+    for (int a = 0; a < RX; ++a) {
+        const int i = l * RX + a;
+        xv[a] = i < NX;
+        const int ii = xv[a] ? i : 0;
+#pragma unroll
+        for (int m = 0; m < NX; ++m) {
+            mAmBKt[a][m] = xv[a] ? stage[OFF_AMBKT + ii + NX * m] : T(0);
+            mA[a][m] = xv[a] ? stage[OFF_A + ii + NX * m] : T(0);
+        }
+#pragma unroll
+        for (int j = 0; j < NU; ++j) {
+            mKt[a][j] = xv[a] ? stage[OFF_K + j + NU * ii] : T(0);  // Kinf^T(i,j) = Kinf(j,i)
+            mB[a][j] = xv[a] ? stage[OFF_B + ii + NX * j] : T(0);
+        }
+        vQd[a] = xv[a] ? stage[OFF_QD + ii] : T(0);
+        vAPf[a] = xv[a] ? stage[OFF_APF + ii] : T(0);
+        vf[a] = xv[a] ? stage[OFF_F + ii] : T(0);
+    }
+#pragma unroll
+    for (int b = 0; b < RU; ++b) {
+        const int j = l * RU + b;
+        uv[b] = j < NU;
+        const int jj = uv[b] ? j : 0;
+#pragma unroll
+        for (int m = 0; m < NX; ++m) {
+            mBt[b][m] = uv[b] ? stage[OFF_B + m + NX * jj] : T(0);  // B^T(j,m) = B(m,j)
+            mK[b][m] = uv[b] ? stage[OFF_K + jj + NU * m] : T(0);
+        }
+#pragma unroll
+        for (int m = 0; m < NU; ++m) mQuu[b][m] = uv[b] ? stage[OFF_QUU + jj + NU * m] : T(0);
+        vRd[b] = uv[b] ? stage[OFF_RD + jj] : T(0);
+        vBPf[b] = uv[b] ? stage[OFF_BPF + jj] : T(0);
+    }
+    // Pinf columns of this lane's rows are only needed once per instance (terminal cost); they stay in global/L1.
+    __syncthreads();  // staging area is reused as state below
+
+    // ---- shared-memory state of this warp: [k][slot a][lane] ----
+    const size_t warp_elems = Cfg::warp_elems(N);
+    T *wbase = reinterpret_cast<T *>(smem_raw) + (size_t)warp * warp_elems;
+    T *sV = wbase;                                // vnew : N   * RX * 32
+    T *sG = sV + (size_t)N * RX * 32;             // g
+    T *sZ = sG + (size_t)N * RX * 32;             // znew : (N-1) * RU * 32
+    T *sY = sZ + (size_t)(N - 1) * RU * 32;       // y
+    T *sD = sY + (size_t)(N - 1) * RU * 32;       // d
+    auto ix = [&](int k, int a) { return ((size_t)k * RX + a) * 32 + lane; };
+    auto iu = [&](int k, int b) { return ((size_t)k * RU + b) * 32 + lane; };
+
+    const bool cold = P.cold != 0;
+    const int64_t ngroups = (P.B + IPW - 1) / IPW;
+    const bool tvb = P.bounds_tv != 0;
+    // time-invariant bounds live in registers
+    T loX[RX], hiX[RX], loU[RU], hiU[RU];
+#pragma unroll
+    for (int a = 0; a < RX; ++a) {
+        loX[a] = (P.en_state_bound && xv[a]) ? __ldg(P.x_min + l * RX + a) : T(0);
+        hiX[a] = (P.en_state_bound && xv[a]) ? __ldg(P.x_max + l * RX + a) : T(0);
+    }
+#pragma unroll
+    for (int b = 0; b < RU; ++b) {
+        loU[b] = (P.en_input_bound && uv[b]) ? __ldg(P.u_min + l * RU + b) : T(0);
+        hiU[b] = (P.en_input_bound && uv[b]) ? __ldg(P.u_max + l * RU + b) : T(0);
+    }
+
+    for (;;) {
+        // ---- next group of IPW instances ----
+        unsigned long long grp = 0;
+        if (lane == 0) grp = atomicAdd(queue, 1ULL);
+        grp = __shfl_sync(0xffffffffu, grp, 0);
+        if ((int64_t)grp >= ngroups) break;
+        const int64_t inst = (int64_t)grp * IPW + slot;
+        const bool live = inst < P.B;
+        const int64_t bi = live ? inst : (P.B - 1);  // clamp so that every address stays valid
+        const int64_t offx = bi * (int64_t)N * NX, offu = bi * (int64_t)(N - 1) * NU;
+        const T *xrefp = P.Xref + (P.xref_pi ? offx : 0);
+        const T *urefp = P.Uref ? P.Uref + (P.uref_pi ? offu : 0) : nullptr;
+
+        // ---- prologue: warm state -> shared memory (coalesced reads of each instance's contiguous block) ----
+        if (!cold) {
+            for (int s = 0; s < IPW; ++s) {
+                const int64_t ib = (int64_t)grp * IPW + s;
+                if (ib >= P.B) break;
+                const int64_t ox = ib * (int64_t)N * NX, ou = ib * (int64_t)(N - 1) * NU;
+                for (int e = lane; e < N * NX; e += 32) {
+                    const int k = e / NX, i = e - k * NX;
+                    const size_t w = ((size_t)k * RX + (i % RX)) * 32 + s * L + i / RX;
+                    sV[w] = P.s_vnew ? P.s_vnew[ox + e] : T(0);
+                    sG[w] = P.s_g ? P.s_g[ox + e] : T(0);
+                }
+                for (int e = lane; e < (N - 1) * NU; e += 32) {
+                    const int k = e / NU, j = e - k * NU;
+                    const size_t w = ((size_t)k * RU + (j % RU)) * 32 + s * L + j / RU;
+                    sZ[w] = P.s_znew ? P.s_znew[ou + e] : T(0);
+                    sY[w] = P.s_y ? P.s_y[ou + e] : T(0);
+                }
+            }
+            __syncwarp();
+        }
+        // x0 (own rows) and the iteration-invariant part of the terminal cost: -(Pinf^T xref_{N-1})
+        T x0o[RX], pterm[RX];
+        {
+            T xr[NX];
+#pragma unroll
+            for (int m = 0; m < NX; ++m) xr[m] = __ldg(xrefp + (int64_t)(N - 1) * NX + m);
+#pragma unroll
+            for (int a = 0; a < RX; ++a) {
+                const int i = l * RX + a, ii = xv[a] ? i : 0;
+                x0o[a] = xv[a] ? __ldg(P.x0 + bi * NX + ii) : T(0);
+                T s = xr[0] * __ldg(P.Pinf_g + 0 + NX * ii);
+#pragma unroll
+                for (int m = 1; m < NX; ++m) s = mac<FAST>(s, xr[m], __ldg(P.Pinf_g + m + NX * ii));
+                pterm[a] = xv[a] ? -s : T(0);
+            }
+        }
+
+        int it_done = 0, solved = 0;
+        bool active = live;
+        T res_px = T(0), res_dx = T(0), res_pu = T(0), res_du = T(0);
+        const bool keep_v = (P.s_v != nullptr) || (P.s_z != nullptr);
+
+        for (int it = 0; it < P.max_iter; ++it) {
+            if (!__any_sync(0xffffffffu, active)) break;
+            const bool zin = cold && it == 0;
+            const bool vin = (!cold) && it == 0;  // work->v / work->z come from the caller on the first iteration
+
+            // ---- terminal cost + backward pass (update_linear_cost fused) ----
+            T po[RX], Pf[NX];
+#pragma unroll
+            for (int a = 0; a < RX; ++a) {
+                const T vn = (zin || !xv[a]) ? T(0) : sV[ix(N - 1, a)], g = (zin || !xv[a]) ? T(0) : sG[ix(N - 1, a)];
+                po[a] = nmac<FAST>(pterm[a], rho, vn - g);
+            }
+            gather<T, RX, L, NX>(po, Pf);
+            // software prefetch of the reference columns (global / L2), one step ahead
+            T xr_n[RX], ur_n[RU];
+#pragma unroll
+            for (int a = 0; a < RX; ++a) xr_n[a] = xv[a] ? __ldg(xrefp + (int64_t)(N - 2) * NX + l * RX + a) : T(0);
+#pragma unroll
+            for (int b = 0; b < RU; ++b) ur_n[b] = (urefp && uv[b]) ? __ldg(urefp + (int64_t)(N - 2) * NU + l * RU + b) : T(0);
+            for (int k = N - 2; k >= 0; --k) {
+                T xr[RX], ur[RU];
+#pragma unroll
+                for (int a = 0; a < RX; ++a) xr[a] = xr_n[a];
+#pragma unroll
+                for (int b = 0; b < RU; ++b) ur[b] = ur_n[b];
+                if (k > 0) {
+#pragma unroll
+                    for (int a = 0; a < RX; ++a) xr_n[a] = xv[a] ? __ldg(xrefp + (int64_t)(k - 1) * NX + l * RX + a) : T(0);
+#pragma unroll
+                    for (int b = 0; b < RU; ++b) ur_n[b] = (urefp && uv[b]) ? __ldg(urefp + (int64_t)(k - 1) * NU + l * RU + b) : T(0);
+                }
+                T q[RX], r[RU], Rf[NU];
+#pragma unroll
+                for (int b = 0; b < RU; ++b) {
+                    const T zn = (zin || !uv[b]) ? T(0) : sZ[iu(k, b)], y = (zin || !uv[b]) ? T(0) : sY[iu(k, b)];
+                    r[b] = nmac<FAST>(-(ur[b] * vRd[b]), rho, zn - y);
+                }
+                gather<T, RU, L, NU>(r, Rf);
+#pragma unroll
+                for (int a = 0; a < RX; ++a) {
+                    const T vn = (zin || !xv[a]) ? T(0) : sV[ix(k, a)], g = (zin || !xv[a]) ? T(0) : sG[ix(k, a)];
+                    q[a] = nmac<FAST>(-(xr[a] * vQd[a]), rho, vn - g);
+                }
+                // d_k = Quu_inv ((B^T p_{k+1} + r_k) + BPf)
+                T s[RU], Sf[NU];
+#pragma unroll
+                for (int b = 0; b < RU; ++b) {
+                    T t = mBt[b][0] * Pf[0];
+#pragma unroll
+                    for (int m = 1; m < NX; ++m) t = mac<FAST>(t, mBt[b][m], Pf[m]);
+                    s[b] = (t + r[b]) + vBPf[b];
+                }
+                gather<T, RU, L, NU>(s, Sf);
+#pragma unroll
+                for (int b = 0; b < RU; ++b) {
+                    T t = mQuu[b][0] * Sf[0];
+#pragma unroll
+                    for (int m = 1; m < NU; ++m) t = mac<FAST>(t, mQuu[b][m], Sf[m]);
+                    if (active && uv[b]) sD[iu(k, b)] = t;
+                }
+                // p_k = ((q_k + AmBKt p_{k+1}) - Kinf^T r_k) + APf
+#pragma unroll
+                for (int a = 0; a < RX; ++a) {
+                    T acc = mAmBKt[a][0] * Pf[0];
+#pragma unroll
+                    for (int m = 1; m < NX; ++m) acc = mac<FAST>(acc, mAmBKt[a][m], Pf[m]);
+                    T kr = mKt[a][0] * Rf[0];
+#pragma unroll
+                    for (int j = 1; j < NU; ++j) kr = mac<FAST>(kr, mKt[a][j], Rf[j]);
+                    po[a] = ((q[a] + acc) - kr) + vAPf[a];
+                }
+                gather<T, RX, L, NX>(po, Pf);
+            }
+            __syncwarp();
+
+            // ---- forward pass fused with slack / dual update / residuals ----
+            T xo[RX], Xf[NX];
+#pragma unroll
+            for (int a = 0; a < RX; ++a) xo[a] = x0o[a];
+            gather<T, RX, L, NX>(xo, Xf);
+            T rpx = T(0), rdx = T(0), rpu = T(0), rdu = T(0);
+            for (int k = 0; k < N; ++k) {
+#pragma unroll
+                for (int a = 0; a < RX; ++a) {
+                    const T g = (zin || !xv[a]) ? T(0) : sG[ix(k, a)];
+                    T vo;
+                    if (vin) vo = (P.s_v && xv[a]) ? P.s_v[offx + (int64_t)k * NX + l * RX + a] : T(0);
+                    else vo = (zin || !xv[a]) ? T(0) : sV[ix(k, a)];
+                    T v = xo[a] + g;
+                    if (P.en_state_bound) {
+                        const T lo = tvb ? (xv[a] ? __ldg(P.x_min + (int64_t)k * NX + l * RX + a) : T(0)) : loX[a];
+                        const T hi = tvb ? (xv[a] ? __ldg(P.x_max + (int64_t)k * NX + l * RX + a) : T(0)) : hiX[a];
+                        v = clamp_ref(v, lo, hi);
+                    }
+                    const T gn = (g + xo[a]) - v;
+                    if (active && xv[a]) {
+                        sV[ix(k, a)] = v;
+                        sG[ix(k, a)] = gn;
+                        if (keep_v && P.s_v) P.s_v[offx + (int64_t)k * NX + l * RX + a] = vo;  // work->v of this iteration
+                    }
+                    const T e1 = tabs(xo[a] - v), e2 = tabs(vo - v);
+                    rpx = (e1 > rpx) ? e1 : rpx;
+                    rdx = (e2 > rdx) ? e2 : rdx;
+                }
+                if (k < N - 1) {
+                    T u[RU], Uf[NU];
+#pragma unroll
+                    for (int b = 0; b < RU; ++b) {
+                        const T d = uv[b] ? sD[iu(k, b)] : T(0);
+                        T t = mK[b][0] * Xf[0];
+#pragma unroll
+                        for (int m = 1; m < NX; ++m) t = mac<FAST>(t, mK[b][m], Xf[m]);
+                        u[b] = (-t) - d;
+                    }
+                    gather<T, RU, L, NU>(u, Uf);
+#pragma unroll
+                    for (int b = 0; b < RU; ++b) {
+                        const T y = (zin || !uv[b]) ? T(0) : sY[iu(k, b)];
+                        T zo;
+                        if (vin) zo = (P.s_z && uv[b]) ? P.s_z[offu + (int64_t)k * NU + l * RU + b] : T(0);
+                        else zo = (zin || !uv[b]) ? T(0) : sZ[iu(k, b)];
+                        T z = u[b] + y;
+                        if (P.en_input_bound) {
+                            const T lo = tvb ? (uv[b] ? __ldg(P.u_min + (int64_t)k * NU + l * RU + b) : T(0)) : loU[b];
+                            const T hi = tvb ? (uv[b] ? __ldg(P.u_max + (int64_t)k * NU + l * RU + b) : T(0)) : hiU[b];
+                            z = clamp_ref(z, lo, hi);
+                        }
+                        const T yn = (y + u[b]) - z;
+                        if (active && uv[b]) {
+                            sZ[iu(k, b)] = z;
+                            sY[iu(k, b)] = yn;
+                            if (keep_v && P.s_z) P.s_z[offu + (int64_t)k * NU + l * RU + b] = zo;
+                        }
+                        const T e1 = tabs(u[b] - z), e2 = tabs(zo - z);
+                        rpu = (e1 > rpu) ? e1 : rpu;
+                        rdu = (e2 > rdu) ? e2 : rdu;
+                    }
+                    // x_{k+1} = (A x_k + B u_k) + f
+#pragma unroll
+                    for (int a = 0; a < RX; ++a) {
+                        T ax = mA[a][0] * Xf[0];
+#pragma unroll
+                        for (int m = 1; m < NX; ++m) ax = mac<FAST>(ax, mA[a][m], Xf[m]);
+                        T bu = mB[a][0] * Uf[0];
+#pragma unroll
+                        for (int j = 1; j < NU; ++j) bu = mac<FAST>(bu, mB[a][j], Uf[j]);
+                        xo[a] = (ax + bu) + vf[a];
+                    }
+                    gather<T, RX, L, NX>(xo, Xf);
+                }
+            }
+            __syncwarp();
+            // ---- termination_condition (admm.cpp:310-328), per instance ----
+            rpx = group_max<T, L>(rpx);
+            rdx = group_max<T, L>(rdx);
+            rpu = group_max<T, L>(rpu);
+            rdu = group_max<T, L>(rdu);
+            if (active) {
+                it_done = it + 1;
+                if (it_done % P.check_termination == 0) {
+                    res_px = rpx;
+                    res_dx = rdx * rho;
+                    res_pu = rpu;
+                    res_du = rdu * rho;
+                    if (res_px < P.pri_tol && res_pu < P.pri_tol && res_dx < P.dua_tol && res_du < P.dua_tol) {
+                        solved = 1;
+                        active = false;
+                    }
+                }
+            }
+        }
+
+        // ---- epilogue ----
+        if (live && l == 0) {
+            if (P.iter) P.iter[inst] = it_done;
+            if (P.solved) P.solved[inst] = solved;
+            if (P.residuals) {
+                T *r = P.residuals + 4 * inst;
+                r[0] = res_px; r[1] = res_dx; r[2] = res_pu; r[3] = res_du;
+            }
+        }
+        // when no iteration ran on a cold start the shared-memory state was never written: define it as zero
+        if (cold && P.max_iter <= 0) {
+            for (size_t w = lane; w < warp_elems; w += 32) wbase[w] = T(0);
+        }
+        __syncwarp();
+        // solution->x = vnew, solution->u = znew; work->vnew/znew/g/y; coalesced transposing copy per instance
+        for (int s = 0; s < IPW; ++s) {
+            const int64_t ib = (int64_t)grp * IPW + s;
+            if (ib >= P.B) break;
+            const int64_t ox = ib * (int64_t)N * NX, ou = ib * (int64_t)(N - 1) * NU;
+            // per-instance flags live in the lanes of slot s
+            const int s_solved = __shfl_sync(0xffffffffu, solved, s * L);
+            const int s_it = __shfl_sync(0xffffffffu, it_done, s * L);
+            for (int e = lane; e < N * NX; e += 32) {
+                const int k = e / NX, i = e - k * NX;
+                const size_t w = ((size_t)k * RX + (i % RX)) * 32 + s * L + i / RX;
+                const T v = sV[w];
+                P.sol_x[ox + e] = v;
+                if (P.s_vnew) P.s_vnew[ox + e] = v;
+                if (P.s_g) P.s_g[ox + e] = sG[w];
+                // work->v: previous vnew if the solve converged (already streamed out during the last forward
+                // pass), else = vnew (admm.cpp:445); untouched when no iteration ran
+                if (P.s_v && !s_solved && s_it > 0) P.s_v[ox + e] = v;
+                else if (P.s_v && cold && s_it == 0) P.s_v[ox + e] = T(0);
+            }
+            for (int e = lane; e < (N - 1) * NU; e += 32) {
+                const int k = e / NU, j = e - k * NU;
+                const size_t w = ((size_t)k * RU + (j % RU)) * 32 + s * L + j / RU;
+                const T z = sZ[w];
+                P.sol_u[ou + e] = z;
+                if (P.s_znew) P.s_znew[ou + e] = z;
+                if (P.s_y) P.s_y[ou + e] = sY[w];
+                if (P.s_z && !s_solved && s_it > 0) P.s_z[ou + e] = z;
+                else if (P.s_z && cold && s_it == 0) P.s_z[ou + e] = T(0);
+            }
+        }
+        // work->x / work->u: replay the last rollout from d and x0 (bit-identical to the last forward pass),
+        // staging it in the (now dead) vnew / znew regions so that the write-back is coalesced too
+        if (P.s_x || P.s_u) {
+            __syncwarp();
+            T xo[RX], Xf[NX];
+#pragma unroll
+            for (int a = 0; a < RX; ++a) xo[a] = x0o[a];
+            gather<T, RX, L, NX>(xo, Xf);
+            const bool ran = it_done > 0;
+            for (int k = 0; k < N; ++k) {
+#pragma unroll
+                for (int a = 0; a < RX; ++a)
+                    if (xv[a]) sV[ix(k, a)] = xo[a];
+                if (k < N - 1) {
+                    T u[RU], Uf[NU];
+#pragma unroll
+                    for (int b = 0; b < RU; ++b) {
+                        const T d = uv[b] ? sD[iu(k, b)] : T(0);
+                        T t = mK[b][0] * Xf[0];
+#pragma unroll
+                        for (int m = 1; m < NX; ++m) t = mac<FAST>(t, mK[b][m], Xf[m]);
+                        u[b] = (-t) - d;
+                        if (uv[b]) sZ[iu(k, b)] = u[b];
+                    }
+                    gather<T, RU, L, NU>(u, Uf);
+#pragma unroll
+                    for (int a = 0; a < RX; ++a) {
+                        T ax = mA[a][0] * Xf[0];
+#pragma unroll
+                        for (int m = 1; m < NX; ++m) ax = mac<FAST>(ax, mA[a][m], Xf[m]);
+                        T bu = mB[a][0] * Uf[0];
+#pragma unroll
+                        for (int j = 1; j < NU; ++j) bu = mac<FAST>(bu, mB[a][j], Uf[j]);
+                        xo[a] = (ax + bu) + vf[a];
+                    }
+                    gather<T, RX, L, NX>(xo, Xf);
+                }
+            }
+            (void)ran;
+            __syncwarp();
+            for (int s = 0; s < IPW; ++s) {
+                const int64_t ib = (int64_t)grp * IPW + s;
+                if (ib >= P.B) break;
+                const int64_t ox = ib * (int64_t)N * NX, ou = ib * (int64_t)(N - 1) * NU;
+                const int s_it = __shfl_sync(0xffffffffu, it_done, s * L);
+                if (P.s_x)
+                    for (int e = lane; e < N * NX; e += 32) {
+                        const int k = e / NX, i = e - k * NX;
+                        const size_t w = ((size_t)k * RX + (i % RX)) * 32 + s * L + i / RX;
+                        if (s_it > 0 || k == 0) P.s_x[ox + e] = sV[w];
+                        else if (cold) P.s_x[ox + e] = T(0);
+                    }
+                if (P.s_u)
+                    for (int e = lane; e < (N - 1) * NU; e += 32) {
+                        const int k = e / NU, j = e - k * NU;
+                        const size_t w = ((size_t)k * RU + (j % RU)) * 32 + s * L + j / RU;
+                        if (s_it > 0) P.s_u[ou + e] = sZ[w];
+                        else if (cold) P.s_u[ou + e] = T(0);
+                    }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side: configuration choice + launch
+// ---------------------------------------------------------------------------------------------------------
+struct GpiPlan {
+    int L = 0, warps = 0;
+    size_t smem = 0;
+};
+
+template <typename T, int NX, int NU, int L>
+inline void gpi_consider(int N, int max_smem, GpiPlan &best) {
+    if constexpr (gpi_feasible<T, NX, NU, L>()) {
+        using Cfg = GpiCfg<NX, NU, L>;
+        const size_t per_warp = Cfg::warp_elems(N) * sizeof(T);
+        // the TMA staging area must fit inside the first warp's region
+        const size_t blob = (size_t)(3 * NX * NX + 2 * NX * NU + NU * NU + 4 * NX + 2 * NU) * sizeof(T) + 32;
+        if (per_warp < blob) return;
+        int w = (int)std::min<size_t>(GPI_MAX_WARPS, (size_t)max_smem / per_warp);
+        if (w < 1) return;
+        // score: instances resident per SM, then fewer lanes per instance (less shuffle traffic)
+        const int inst = w * Cfg::IPW, binst = best.warps * (best.L ? 32 / best.L : 0);
+        const bool better = best.L == 0 || (w >= 4 && best.warps < 4) || (((w >= 4) == (best.warps >= 4)) && inst > binst);
+        if (better) {
+            best.L = L;
+            best.warps = w;
+            best.smem = per_warp * w;
+        }
+    }
+}
+
+template <typename T, int NX, int NU>
+inline GpiPlan gpi_plan(int N, int max_smem) {
+    GpiPlan p;
+    gpi_consider<T, NX, NU, 4>(N, max_smem, p);
+    gpi_consider<T, NX, NU, 8>(N, max_smem, p);
+    gpi_consider<T, NX, NU, 16>(N, max_smem, p);
+    return p;
+}
+
+template <typename T, int NX, int NU>
+inline int gpi_fit_T(int N, int max_smem) {
+    return (int)gpi_plan<T, NX, NU>(N, max_smem).smem;
+}
+
+template <typename T, int NX, int NU, int L, bool FAST>
+int launch_gpi_L(LaunchDesc *d, const GpiPlan &plan, const KParams<T, NX, NU> &P, const T *gmat) {
+    if constexpr (gpi_feasible<T, NX, NU, L>()) {
+        auto kern = gpi_solve_kernel<T, NX, NU, L, FAST>;
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem) != cudaSuccess)
+            return TINYMPC_ERR_CUDA;
+        const int64_t ngroups = (d->io.B + (32 / L) - 1) / (32 / L);
+        const int64_t want = (ngroups + plan.warps - 1) / plan.warps;
+        const int ctas = (int)std::max<int64_t>(1, std::min<int64_t>(d->sm_count, want));
+        kern<<<ctas, plan.warps * 32, plan.smem, d->stream>>>(P, gmat, (unsigned long long *)d->work_queue);
+        d->out_threads = plan.warps * 32;
+        d->out_ctas = ctas;
+        d->out_smem = (int)plan.smem;
+        d->out_lanes_per_instance = L;
+        d->out_instances_per_cta = plan.warps * (32 / L);
+        return cudaGetLastError() == cudaSuccess ? TINYMPC_OK : TINYMPC_ERR_CUDA;
+    } else {
+        return TINYMPC_ERR_UNSUPPORTED;
+    }
+}
+
+}  // namespace tmpc

@@ -1,0 +1,345 @@
+#!/usr/bin/env python3
+"""bench.py — the contract benchmark of the batched TinyMPC solve path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1], the configuration the metric is quoted on): quadrotor_hovering
+(nx=12, nu=4, N=50, box constraints, quadrotor_20hz data), batch = 65536 identical instances per GPU, fp32,
+cold start, max_iter=100, tolerances 1e-3.  One "step" = one batched tiny_solve() of the whole batch.
+This instance does not converge in the reference either: every instance runs the full 100 ADMM
+iterations, so the metric "instances solved/s" is "instances terminated/s by the reference's rule", and
+ADMM iterations/s/GPU is reported next to it.  Arithmetic mode: STRICT (bit-identical to the pinned reference).
+
+value  : device-resident throughput, inputs already in HBM, CUDA events on the launch stream, per-step events,
+         L2 flushed (256 MiB write) between timed steps, max over ranks.
+e2e    : the same metric through the public host API (BatchedTinySolver.solve_prepared -> tinympc_b200_solve_host):
+         pinned host inputs copied H2D and the complete solution copied D2H inside the timed region, every step.
+roofline, cpu_baseline, clocks: see DESIGN.md §7.
+
+--impl reference times the reference's own CPU implementation (oracle/_ref = the unmodified reference compiled
+here; falls back to the oracle port when the prebuilt library is absent) on the host cores, same metric/config.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = "quadrotor_hovering nx=12 nu=4 N=50 box batch=65536/GPU identical instances fp32 cold-start max_iter=100 (BASELINE configs[1])"
+METRIC = "MPC instances solved/sec (terminated by the reference rule; ADMM iters/sec/GPU alongside)"
+B_PER_GPU = 65536
+N_HORIZON = 50
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default="strict", choices=["strict", "fast"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "tpi", "gpi"])
+    ap.add_argument("--cpu-sample", type=int, default=16384, help="instances in the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own implementation on the host cores (oracle/_ref), or the oracle port
+# ---------------------------------------------------------------------------------------------------------
+def cpu_arm(sample, steps, warmup, prob_from_product=None):
+    """Returns dict(value inst/s, iters_per_s, kind, cores, sample, variant, ms_per_step)."""
+    from oracle import oracle
+    from tinympc_b200 import workloads as wl
+
+    spec = wl.quadrotor(N=N_HORIZON)
+    dt = np.float32
+    cores = os.cpu_count() or 1
+    inst = wl.hovering_instances(sample, N=N_HORIZON, dtype=dt)
+    variants = [v for v in ("fast", "fastv3") if oracle.ref_available(dt, v)]
+    if variants:
+        kind = "reference"
+        prob = oracle.ref_setup(spec.nx, spec.nu, spec.N, spec.rho, spec.A, spec.B, spec.f, spec.Qdiag, spec.Rdiag, dtype=dt,
+                                variant=variants[0], **spec.constraints)
+
+        def run(n, variant, threads):
+            return oracle.solve_batch(prob, spec.settings, inst["x0"][:n], inst["Xref"], None, cold_start=True,
+                                      impl="reference", variant=variant, nthreads=threads)
+        # pick the faster build of the reference (SSE2 vs AVX2+FMA) on a small calibration run
+        best, best_t = variants[0], 1e30
+        for v in variants:
+            n = min(sample, 64 * cores)
+            t0 = time.perf_counter()
+            run(n, v, cores)
+            t = time.perf_counter() - t0
+            if t < best_t:
+                best, best_t = v, t
+        variant = best
+    else:
+        kind, variant = "port", "oracle/tinympc_oracle.c -O2 -ffp-contract=off"
+        prob = oracle.port_setup(spec.nx, spec.nu, spec.N, spec.rho, spec.A, spec.B, spec.f, spec.Qdiag, spec.Rdiag, dtype=dt,
+                                 **spec.constraints)
+
+        def run(n, variant, threads):
+            return oracle.solve_batch(prob, spec.settings, inst["x0"][:n], inst["Xref"], None, cold_start=True,
+                                      impl="port", nthreads=threads)
+    for _ in range(warmup):
+        run(min(sample, 64 * cores), variant, cores)
+    t0 = time.perf_counter()
+    iters = 0
+    for _ in range(steps):
+        r = run(sample, variant, cores)
+        iters += int(r["iter"].sum())
+    dtm = time.perf_counter() - t0
+    return dict(value=sample * steps / dtm, iters_per_s=iters / dtm, kind=kind, cores=cores, variant=variant,
+                sample=f"{sample} of the 65536 instances per step ({sample * 100} ADMM iterations), {steps} step(s), "
+                       f"{cores} host threads, one TinySolver per thread, fp32 build '{variant}'",
+                ms_per_step=dtm / steps * 1e3, unit="instances/s")
+
+
+def reference_main(args, rank, world):
+    if rank != 0:
+        return
+    sample = min(args.cpu_sample, 8192)
+    r = cpu_arm(sample, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "instances/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "arm": "reference CPU implementation on the host cores (bounded sample per step)"},
+        "admm_iters_per_s": r["iters_per_s"],
+        "cpu_baseline": {"value": r["value"], "unit": "instances/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": "instances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi, the recipe's query)
+# ---------------------------------------------------------------------------------------------------------
+class Clocks:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append((time.perf_counter(), ln.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons, power = [], None, set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for t, ln in self.rows:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                if t0 - 0.05 <= t <= t1 + 0.05:
+                    sm.append(float(p[1]))
+                    power.append(float(p[3]))
+                    for n, v in zip(names, p[5:9]):
+                        if v.lower().startswith("active"):
+                            reasons.add(n)
+                smax = float(p[2])
+            except ValueError:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power) if power else None}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_main(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from tinympc_b200 import abi, workloads as wl
+    from tinympc_b200.batch import HostBatch
+    from tinympc_b200.parallel import reduce_stats
+    from tinympc_b200.solver import BatchedTinySolver, setup_problem
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    K, W = args.steps, max(3, args.warmup)
+    B = B_PER_GPU
+    spec = wl.quadrotor(N=N_HORIZON)
+    dt = np.float32
+    prob = setup_problem(spec, dt)
+    mode = abi.MODE_STRICT if args.mode == "strict" else abi.MODE_FAST
+    kern = dict(auto=abi.KERNEL_AUTO, tpi=abi.KERNEL_TPI, gpi=abi.KERNEL_GPI)[args.kernel]
+    solver = BatchedTinySolver(prob, spec.settings, device=local, mode=mode, kernel=kern)
+    inst = wl.hovering_instances(B, N=N_HORIZON, dtype=dt)
+
+    # ---- device-resident arm ----
+    batch, out = solver.make_device_batch(inst["x0"], inst["Xref"], None, cold_start=True)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    stream = torch.cuda.current_stream(dev)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    for _ in range(W):
+        solver.solve_device(batch, stream)
+    torch.cuda.synchronize(dev)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    clocks = Clocks(local)
+    clocks.start()
+    time.sleep(0.25)
+    barrier()
+    t_wall0 = time.perf_counter()
+    kernel_ms = []
+    for i in range(K):
+        flush.zero_()
+        ev[i][0].record(stream)
+        solver.solve_device(batch, stream)
+        ev[i][1].record(stream)
+    barrier()
+    t_wall1 = time.perf_counter()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    kernel_ms.append(solver.stats()["kernel_ms"])
+    total_ms = float(sum(step_ms))
+    st = solver.stats()
+    iters_step = int(out["iter"].sum().item())
+    solved_step = int(out["solved"].sum().item())
+    res_max = out["residuals"].max(dim=0).values.double().cpu().tolist()
+    red = reduce_stats(dict(instances=B * K, solved=solved_step * K, iters=iters_step * K, res_max=res_max, ms=total_ms),
+                       device=dev if world > 1 else None)
+    launches = K * st["kernel_launches"]
+
+    # ---- end-to-end arm: public host API, pinned host buffers, H2D + D2H inside the timed region ----
+    hb = HostBatch(prob, inst["x0"], inst["Xref"], None, cold_start=True)
+    pins = {}
+    for name in ("x0", "sol_x", "sol_u", "iter", "solved", "residuals"):
+        a = getattr(hb, name)
+        tpin = torch.from_numpy(np.array(a, copy=True)).pin_memory()
+        pins[name] = tpin
+        setattr(hb, name, tpin.numpy())
+    cb = hb.to_c()
+    for _ in range(W):
+        solver.solve_prepared(hb, cb)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        solver.solve_prepared(hb, cb)
+    torch.cuda.synchronize(dev)
+    e2e_ms_local = (time.perf_counter() - t0) * 1e3
+    e2e_launches = solver.stats()["kernel_launches"]
+    if world > 1:
+        tmax = torch.tensor([e2e_ms_local], dtype=torch.float64, device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        e2e_ms = float(tmax.item())
+    else:
+        e2e_ms = e2e_ms_local
+    clk = clocks.stop(t_wall0, time.perf_counter())
+    h2d = int(hb.x0.nbytes + hb.Xref.nbytes)
+    d2h = int(hb.sol_x.nbytes + hb.sol_u.nbytes + hb.iter.nbytes + hb.solved.nbytes + hb.residuals.nbytes)
+    e2e_ok = bool(np.array_equal(hb.sol_u.view(np.uint8), out["sol_u"].cpu().numpy().view(np.uint8)))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (the solve kernel is the only kernel of a step) ----
+    s = 4
+    nN, mN = 12 * N_HORIZON, 4 * (N_HORIZON - 1)
+    bytes_inst = s * 12 + s * (nN + mN) + 4 * s + 8  # x0 + solution x,u + 4 residuals + iter + solved   = 3256
+    bytes_shared = s * (1 + 2 * 12 * 4 + 3 * 144 + 16 + 3 * 12 + 2 * 4 + 2 * (nN + mN))
+    alg_bytes = B * bytes_inst + st["ctas"] * bytes_shared
+    k_ms = float(np.mean(step_ms))  # one launch per step: the step IS the kernel
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(f"family{st['kernel_family']}_{args.mode}")
+        except Exception:
+            traffic = None
+    F_iter = 64560
+    flops = red["iters"] / world * F_iter / (total_ms * 1e-3)  # per GPU
+    line = {
+        "metric": METRIC, "value": world * B * K / (red["ms"] * 1e-3), "unit": "instances/s", "n_gpus": world, "steps": K,
+        "warmup": W, "ms_per_step": red["ms"] / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "mode": args.mode, "kernel": {1: "tpi", 2: "gpi"}[st["kernel_family"]],
+                   "l2": "flushed (256 MiB write) between timed steps", "parallelism": f"batch-sharded x{world}, no data-path collective",
+                   "lanes_per_instance": st["lanes_per_instance"], "ctas": st["ctas"], "threads_per_cta": st["threads_per_cta"],
+                   "smem_bytes_per_cta": st["smem_bytes_per_cta"]},
+        "admm_iters_per_s_per_gpu": red["iters"] / world / (red["ms"] * 1e-3),
+        "solved_fraction": red["solved"] / red["instances"],
+        "residual_max": red["res_max"],
+        "gpu_launches": launches,
+        "e2e": {"value": world * B * K / (e2e_ms * 1e-3), "unit": "instances/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms / K, "kernel_launches_per_step": e2e_launches, "matches_device_arm": e2e_ok},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                     "kernel_ms": k_ms,
+                     "note": "compute/latency-bound by construction (SURVEY §8d); secondary: fp32 pipe",
+                     "flops_achieved_tflops": flops / 1e12, "flops_frac_of_74.5_tflops_fp32": flops / 74.5e12},
+        "clocks": clk,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            c = cpu_arm(args.cpu_sample, 1, 1)
+            line["cpu_baseline"] = {"value": c["value"], "unit": "instances/s", "cores": c["cores"], "kind": c["kind"], "sample": c["sample"],
+                                    "admm_iters_per_s": c["iters_per_s"]}
+        except Exception as e:  # the checker libraries are optional for the product arm
+            line["cpu_baseline"] = {"value": None, "unit": "instances/s", "cores": os.cpu_count(), "kind": "unavailable", "sample": str(e)}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

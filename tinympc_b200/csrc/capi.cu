@@ -477,7 +477,18 @@ struct Field {
     size_t per_inst;   // bytes per instance
     bool is_in, is_out;
     void **dev_slot;   // where the device pointer goes in the device-side tinympc_batch_t
+    bool pinned = false;  // the caller's buffer is page-locked: DMA straight from/to it, no staging copy
 };
+
+bool is_pinned(const void *p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
 
 }  // namespace
 
@@ -542,6 +553,7 @@ int tinympc_b200_solve_host(tinympc_b200_solver_t *s, const tinympc_batch_t *io)
     if (io->solved) fields.push_back({nullptr, io->solved, sizeof(int32_t), false, true, (void **)&dev.solved});
     if (io->residuals) fields.push_back({nullptr, io->residuals, 4 * es, false, true, (void **)&dev.residuals});
 
+    for (Field &f : fields) f.pinned = is_pinned(f.is_out ? f.dst : f.src) && (!f.is_in || !f.src || is_pinned(f.src));
     size_t per_inst_dev = 0, per_inst_in = 0, per_inst_out = 0;
     for (const Field &f : fields) {
         per_inst_dev += f.per_inst;
@@ -575,7 +587,7 @@ int tinympc_b200_solve_host(tinympc_b200_solver_t *s, const tinympc_batch_t *io)
         char *po = (char *)s->pin_out[slot].p;
         for (const Field &f : fields) {
             if (!f.is_out) continue;
-            std::memcpy((char *)f.dst + f.per_inst * pend[slot].b0, po, f.per_inst * pend[slot].nb);
+            if (!f.pinned) std::memcpy((char *)f.dst + f.per_inst * pend[slot].b0, po, f.per_inst * pend[slot].nb);
             po += padded(f.per_inst * chunk);
         }
         pend[slot].active = false;
@@ -603,8 +615,12 @@ int tinympc_b200_solve_host(tinympc_b200_solver_t *s, const tinympc_batch_t *io)
             char *cur = pd;
             for (const Field &f : fields) {
                 if (f.is_in && f.src) {
-                    std::memcpy(pi, (const char *)f.src + f.per_inst * b0, f.per_inst * nb);
-                    CUDA_TRY(cudaMemcpyAsync(cur, pi, f.per_inst * nb, cudaMemcpyHostToDevice, s->st_h2d));
+                    const char *hsrc = (const char *)f.src + f.per_inst * b0;
+                    if (!f.pinned) {
+                        std::memcpy(pi, hsrc, f.per_inst * nb);
+                        hsrc = pi;
+                    }
+                    CUDA_TRY(cudaMemcpyAsync(cur, hsrc, f.per_inst * nb, cudaMemcpyHostToDevice, s->st_h2d));
                     pi += padded(f.per_inst * chunk);
                 }
                 cur += padded(f.per_inst * chunk);
@@ -620,7 +636,8 @@ int tinympc_b200_solve_host(tinympc_b200_solver_t *s, const tinympc_batch_t *io)
             char *cur = pd, *po = (char *)s->pin_out[slot].p;
             for (const Field &f : fields) {
                 if (f.is_out) {
-                    CUDA_TRY(cudaMemcpyAsync(po, cur, f.per_inst * nb, cudaMemcpyDeviceToHost, s->st_d2h));
+                    char *hdst = f.pinned ? (char *)f.dst + f.per_inst * b0 : po;
+                    CUDA_TRY(cudaMemcpyAsync(hdst, cur, f.per_inst * nb, cudaMemcpyDeviceToHost, s->st_d2h));
                     po += padded(f.per_inst * chunk);
                 }
                 cur += padded(f.per_inst * chunk);

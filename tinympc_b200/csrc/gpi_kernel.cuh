@@ -63,16 +63,36 @@ __device__ __forceinline__ T group_max(T v) {
 
 constexpr int GPI_MAX_WARPS = 8;
 
+template <bool B>
+struct BoolTag {
+    static constexpr bool value = B;
+};
+
+// Box clamp.  STRICT keeps Eigen's compare-select form (differs from fmax/fmin only in the sign of a zero
+// result when a bound is a signed zero); FAST uses the single-instruction min/max.
+template <bool FAST, typename T>
+__device__ __forceinline__ T clamp_box(T v, T lo, T hi) {
+    if constexpr (FAST) {
+        return fmin(fmax(v, lo), hi);
+    } else {
+        return clamp_ref(v, lo, hi);
+    }
+}
+// max(m, |d|): identical to the oracle's (|d| > m) ? |d| : m  because m is never NaN and |d| >= +0
+__device__ __forceinline__ float absmax(float m, float d) { return fmaxf(m, fabsf(d)); }
+__device__ __forceinline__ double absmax(double m, double d) { return fmax(m, fabs(d)); }
+
 template <typename T, int NX, int NU, int L, bool FAST>
 __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
     gpi_solve_kernel(const __grid_constant__ KParams<T, NX, NU> P, const T *__restrict__ gmat, unsigned long long *queue) {
     using Cfg = GpiCfg<NX, NU, L>;
     constexpr int RX = Cfg::RX, RU = Cfg::RU, IPW = Cfg::IPW;
+    constexpr bool EXACT = (RX * L == NX) && (RU * L == NU);  // no padding rows: predicates vanish
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = P.N;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int l = lane % L;         // lane inside the instance group
-    const int slot = lane / L;      // which of the warp's instances
+    const int l = lane % L;     // lane inside the instance group
+    const int slot = lane / L;  // which of the warp's instances
     const T rho = P.rho;
 
     // ---- stage the cache blob (A, B, f, Qd, Rd, Kinf, Pinf, Quu, AmBKt, APf, BPf) into shared memory with
@@ -115,7 +135,7 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
 #pragma unroll
     for (int a = 0; a < RX; ++a) {
         const int i = l * RX + a;
-        xv[a] = i < NX;
+        xv[a] = EXACT || (i < NX);
         const int ii = xv[a] ? i : 0;
 #pragma unroll
         for (int m = 0; m < NX; ++m) {
@@ -134,7 +154,7 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
 #pragma unroll
     for (int b = 0; b < RU; ++b) {
         const int j = l * RU + b;
-        uv[b] = j < NU;
+        uv[b] = EXACT || (j < NU);
         const int jj = uv[b] ? j : 0;
 #pragma unroll
         for (int m = 0; m < NX; ++m) {
@@ -146,35 +166,34 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
         vRd[b] = uv[b] ? stage[OFF_RD + jj] : T(0);
         vBPf[b] = uv[b] ? stage[OFF_BPF + jj] : T(0);
     }
-    // Pinf columns of this lane's rows are only needed once per instance (terminal cost); they stay in global/L1.
     __syncthreads();  // staging area is reused as state below
 
-    // ---- shared-memory state of this warp: [k][slot a][lane] ----
-    const size_t warp_elems = Cfg::warp_elems(N);
+    // ---- shared-memory state of this warp: [k][slot a][lane]; element offsets fit in 32 bits ----
+    const int warp_elems = (int)Cfg::warp_elems(N);
     T *wbase = reinterpret_cast<T *>(smem_raw) + (size_t)warp * warp_elems;
-    T *sV = wbase;                                // vnew : N   * RX * 32
-    T *sG = sV + (size_t)N * RX * 32;             // g
-    T *sZ = sG + (size_t)N * RX * 32;             // znew : (N-1) * RU * 32
-    T *sY = sZ + (size_t)(N - 1) * RU * 32;       // y
-    T *sD = sY + (size_t)(N - 1) * RU * 32;       // d
-    auto ix = [&](int k, int a) { return ((size_t)k * RX + a) * 32 + lane; };
-    auto iu = [&](int k, int b) { return ((size_t)k * RU + b) * 32 + lane; };
+    T *sV = wbase + lane;                 // vnew : N * RX * 32
+    T *sG = sV + N * RX * 32;             // g
+    T *sZ = sG + N * RX * 32;             // znew : (N-1) * RU * 32
+    T *sY = sZ + (N - 1) * RU * 32;       // y
+    T *sD = sY + (N - 1) * RU * 32;       // d
+    constexpr int SX = RX * 32, SU = RU * 32;  // per-k strides
 
     const bool cold = P.cold != 0;
     const int64_t ngroups = (P.B + IPW - 1) / IPW;
     const bool tvb = P.bounds_tv != 0;
-    // time-invariant bounds live in registers
-    T loX[RX], hiX[RX], loU[RU], hiU[RU];
+    const bool enx = P.en_state_bound != 0, enu = P.en_input_bound != 0;
+    T loX[RX], hiX[RX], loU[RU], hiU[RU];  // bounds of this lane's rows (reloaded per k only if time-varying)
 #pragma unroll
     for (int a = 0; a < RX; ++a) {
-        loX[a] = (P.en_state_bound && xv[a]) ? __ldg(P.x_min + l * RX + a) : T(0);
-        hiX[a] = (P.en_state_bound && xv[a]) ? __ldg(P.x_max + l * RX + a) : T(0);
+        loX[a] = (enx && xv[a]) ? __ldg(P.x_min + l * RX + a) : T(0);
+        hiX[a] = (enx && xv[a]) ? __ldg(P.x_max + l * RX + a) : T(0);
     }
 #pragma unroll
     for (int b = 0; b < RU; ++b) {
-        loU[b] = (P.en_input_bound && uv[b]) ? __ldg(P.u_min + l * RU + b) : T(0);
-        hiU[b] = (P.en_input_bound && uv[b]) ? __ldg(P.u_max + l * RU + b) : T(0);
+        loU[b] = (enu && uv[b]) ? __ldg(P.u_min + l * RU + b) : T(0);
+        hiU[b] = (enu && uv[b]) ? __ldg(P.u_max + l * RU + b) : T(0);
     }
+    const bool keep_v = (P.s_v != nullptr) || (P.s_z != nullptr);
 
     for (;;) {
         // ---- next group of IPW instances ----
@@ -186,36 +205,42 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
         const bool live = inst < P.B;
         const int64_t bi = live ? inst : (P.B - 1);  // clamp so that every address stays valid
         const int64_t offx = bi * (int64_t)N * NX, offu = bi * (int64_t)(N - 1) * NU;
-        const T *xrefp = P.Xref + (P.xref_pi ? offx : 0);
-        const T *urefp = P.Uref ? P.Uref + (P.uref_pi ? offu : 0) : nullptr;
+        const T *xrefp = P.Xref + (P.xref_pi ? offx : 0) + l * RX;
+        const T *urefp = P.Uref ? P.Uref + (P.uref_pi ? offu : 0) + l * RU : nullptr;
 
-        // ---- prologue: warm state -> shared memory (coalesced reads of each instance's contiguous block) ----
-        if (!cold) {
+        // ---- prologue: zero (cold) or load (warm) the shared-memory state ----
+        if (cold) {
+            float4 *w4 = reinterpret_cast<float4 *>(wbase);
+            const int n4 = (int)((size_t)warp_elems * sizeof(T) / 16);
+            for (int w = lane; w < n4; w += 32) w4[w] = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+            T *uV = wbase, *uG = uV + N * SX, *uZ = uG + N * SX, *uY = uZ + (N - 1) * SU;
             for (int s = 0; s < IPW; ++s) {
                 const int64_t ib = (int64_t)grp * IPW + s;
                 if (ib >= P.B) break;
                 const int64_t ox = ib * (int64_t)N * NX, ou = ib * (int64_t)(N - 1) * NU;
                 for (int e = lane; e < N * NX; e += 32) {
                     const int k = e / NX, i = e - k * NX;
-                    const size_t w = ((size_t)k * RX + (i % RX)) * 32 + s * L + i / RX;
-                    sV[w] = P.s_vnew ? P.s_vnew[ox + e] : T(0);
-                    sG[w] = P.s_g ? P.s_g[ox + e] : T(0);
+                    const int w = (k * RX + (i % RX)) * 32 + s * L + i / RX;
+                    uV[w] = P.s_vnew ? P.s_vnew[ox + e] : T(0);
+                    uG[w] = P.s_g ? P.s_g[ox + e] : T(0);
                 }
                 for (int e = lane; e < (N - 1) * NU; e += 32) {
                     const int k = e / NU, j = e - k * NU;
-                    const size_t w = ((size_t)k * RU + (j % RU)) * 32 + s * L + j / RU;
-                    sZ[w] = P.s_znew ? P.s_znew[ou + e] : T(0);
-                    sY[w] = P.s_y ? P.s_y[ou + e] : T(0);
+                    const int w = (k * RU + (j % RU)) * 32 + s * L + j / RU;
+                    uZ[w] = P.s_znew ? P.s_znew[ou + e] : T(0);
+                    uY[w] = P.s_y ? P.s_y[ou + e] : T(0);
                 }
             }
-            __syncwarp();
         }
+        __syncwarp();
         // x0 (own rows) and the iteration-invariant part of the terminal cost: -(Pinf^T xref_{N-1})
         T x0o[RX], pterm[RX];
         {
             T xr[NX];
+            const T *xl = xrefp - l * RX + (int64_t)(N - 1) * NX;
 #pragma unroll
-            for (int m = 0; m < NX; ++m) xr[m] = __ldg(xrefp + (int64_t)(N - 1) * NX + m);
+            for (int m = 0; m < NX; ++m) xr[m] = __ldg(xl + m);
 #pragma unroll
             for (int a = 0; a < RX; ++a) {
                 const int i = l * RX + a, ii = xv[a] ? i : 0;
@@ -230,144 +255,124 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
         int it_done = 0, solved = 0;
         bool active = live;
         T res_px = T(0), res_dx = T(0), res_pu = T(0), res_du = T(0);
-        const bool keep_v = (P.s_v != nullptr) || (P.s_z != nullptr);
 
-        for (int it = 0; it < P.max_iter; ++it) {
-            if (!__any_sync(0xffffffffu, active)) break;
-            const bool zin = cold && it == 0;
-            const bool vin = (!cold) && it == 0;  // work->v / work->z come from the caller on the first iteration
-
-            // ---- terminal cost + backward pass (update_linear_cost fused) ----
-            T po[RX], Pf[NX];
+        // linear cost of column k for this lane's rows: q = -(xref*Qd) - rho*(vnew - g), r = -(uref*Rd) - rho*(znew - y)
+        auto cost_x = [&](int k, T (&q)[RX]) {
 #pragma unroll
             for (int a = 0; a < RX; ++a) {
-                const T vn = (zin || !xv[a]) ? T(0) : sV[ix(N - 1, a)], g = (zin || !xv[a]) ? T(0) : sG[ix(N - 1, a)];
-                po[a] = nmac<FAST>(pterm[a], rho, vn - g);
+                const T xr = xv[a] ? __ldg(xrefp + (int64_t)k * NX + a) : T(0);
+                const T vn = xv[a] ? sV[k * SX + a * 32] : T(0), g = xv[a] ? sG[k * SX + a * 32] : T(0);
+                q[a] = nmac<FAST>(-(xr * vQd[a]), rho, vn - g);
             }
-            gather<T, RX, L, NX>(po, Pf);
-            // software prefetch of the reference columns (global / L2), one step ahead
-            T xr_n[RX], ur_n[RU];
+        };
+        auto cost_u = [&](int k, T (&r)[RU]) {
 #pragma unroll
-            for (int a = 0; a < RX; ++a) xr_n[a] = xv[a] ? __ldg(xrefp + (int64_t)(N - 2) * NX + l * RX + a) : T(0);
-#pragma unroll
-            for (int b = 0; b < RU; ++b) ur_n[b] = (urefp && uv[b]) ? __ldg(urefp + (int64_t)(N - 2) * NU + l * RU + b) : T(0);
-            for (int k = N - 2; k >= 0; --k) {
-                T xr[RX], ur[RU];
-#pragma unroll
-                for (int a = 0; a < RX; ++a) xr[a] = xr_n[a];
-#pragma unroll
-                for (int b = 0; b < RU; ++b) ur[b] = ur_n[b];
-                if (k > 0) {
-#pragma unroll
-                    for (int a = 0; a < RX; ++a) xr_n[a] = xv[a] ? __ldg(xrefp + (int64_t)(k - 1) * NX + l * RX + a) : T(0);
-#pragma unroll
-                    for (int b = 0; b < RU; ++b) ur_n[b] = (urefp && uv[b]) ? __ldg(urefp + (int64_t)(k - 1) * NU + l * RU + b) : T(0);
-                }
-                T q[RX], r[RU], Rf[NU];
-#pragma unroll
-                for (int b = 0; b < RU; ++b) {
-                    const T zn = (zin || !uv[b]) ? T(0) : sZ[iu(k, b)], y = (zin || !uv[b]) ? T(0) : sY[iu(k, b)];
-                    r[b] = nmac<FAST>(-(ur[b] * vRd[b]), rho, zn - y);
-                }
-                gather<T, RU, L, NU>(r, Rf);
-#pragma unroll
-                for (int a = 0; a < RX; ++a) {
-                    const T vn = (zin || !xv[a]) ? T(0) : sV[ix(k, a)], g = (zin || !xv[a]) ? T(0) : sG[ix(k, a)];
-                    q[a] = nmac<FAST>(-(xr[a] * vQd[a]), rho, vn - g);
-                }
-                // d_k = Quu_inv ((B^T p_{k+1} + r_k) + BPf)
-                T s[RU], Sf[NU];
-#pragma unroll
-                for (int b = 0; b < RU; ++b) {
-                    T t = mBt[b][0] * Pf[0];
-#pragma unroll
-                    for (int m = 1; m < NX; ++m) t = mac<FAST>(t, mBt[b][m], Pf[m]);
-                    s[b] = (t + r[b]) + vBPf[b];
-                }
-                gather<T, RU, L, NU>(s, Sf);
-#pragma unroll
-                for (int b = 0; b < RU; ++b) {
-                    T t = mQuu[b][0] * Sf[0];
-#pragma unroll
-                    for (int m = 1; m < NU; ++m) t = mac<FAST>(t, mQuu[b][m], Sf[m]);
-                    if (active && uv[b]) sD[iu(k, b)] = t;
-                }
-                // p_k = ((q_k + AmBKt p_{k+1}) - Kinf^T r_k) + APf
-#pragma unroll
-                for (int a = 0; a < RX; ++a) {
-                    T acc = mAmBKt[a][0] * Pf[0];
-#pragma unroll
-                    for (int m = 1; m < NX; ++m) acc = mac<FAST>(acc, mAmBKt[a][m], Pf[m]);
-                    T kr = mKt[a][0] * Rf[0];
-#pragma unroll
-                    for (int j = 1; j < NU; ++j) kr = mac<FAST>(kr, mKt[a][j], Rf[j]);
-                    po[a] = ((q[a] + acc) - kr) + vAPf[a];
-                }
-                gather<T, RX, L, NX>(po, Pf);
+            for (int b = 0; b < RU; ++b) {
+                const T ur = (urefp && uv[b]) ? __ldg(urefp + (int64_t)k * NU + b) : T(0);
+                const T zn = uv[b] ? sZ[k * SU + b * 32] : T(0), y = uv[b] ? sY[k * SU + b * 32] : T(0);
+                r[b] = nmac<FAST>(-(ur * vRd[b]), rho, zn - y);
             }
-            __syncwarp();
+        };
 
-            // ---- forward pass fused with slack / dual update / residuals ----
+        // forward pass fused with slack / dual update / residuals.  SLOW = first iteration of a warm start
+        // (work->v / work->z come from the caller) or work->v / work->z are being persisted.
+        auto forward = [&](auto tag, const bool vin, T &rpx, T &rdx, T &rpu, T &rdu) {
+            constexpr bool SLOW = decltype(tag)::value;
             T xo[RX], Xf[NX];
 #pragma unroll
             for (int a = 0; a < RX; ++a) xo[a] = x0o[a];
             gather<T, RX, L, NX>(xo, Xf);
-            T rpx = T(0), rdx = T(0), rpu = T(0), rdu = T(0);
+            T gc[RX], vc[RX], yc[RU], zc[RU], dc[RU];  // state of the current column (prefetched)
+#pragma unroll
+            for (int a = 0; a < RX; ++a) {
+                gc[a] = xv[a] ? sG[a * 32] : T(0);
+                vc[a] = xv[a] ? sV[a * 32] : T(0);
+            }
+#pragma unroll
+            for (int b = 0; b < RU; ++b) {
+                yc[b] = uv[b] ? sY[b * 32] : T(0);
+                zc[b] = uv[b] ? sZ[b * 32] : T(0);
+                dc[b] = uv[b] ? sD[b * 32] : T(0);
+            }
             for (int k = 0; k < N; ++k) {
+                // prefetch the next column's state while this one is being processed
+                T gn_[RX], vn_[RX], yn_[RU], zn_[RU], dn_[RU];
+                const bool more = k + 1 < N, moreu = k + 2 < N;
 #pragma unroll
                 for (int a = 0; a < RX; ++a) {
-                    const T g = (zin || !xv[a]) ? T(0) : sG[ix(k, a)];
-                    T vo;
-                    if (vin) vo = (P.s_v && xv[a]) ? P.s_v[offx + (int64_t)k * NX + l * RX + a] : T(0);
-                    else vo = (zin || !xv[a]) ? T(0) : sV[ix(k, a)];
-                    T v = xo[a] + g;
-                    if (P.en_state_bound) {
-                        const T lo = tvb ? (xv[a] ? __ldg(P.x_min + (int64_t)k * NX + l * RX + a) : T(0)) : loX[a];
-                        const T hi = tvb ? (xv[a] ? __ldg(P.x_max + (int64_t)k * NX + l * RX + a) : T(0)) : hiX[a];
-                        v = clamp_ref(v, lo, hi);
-                    }
-                    const T gn = (g + xo[a]) - v;
-                    if (active && xv[a]) {
-                        sV[ix(k, a)] = v;
-                        sG[ix(k, a)] = gn;
-                        if (keep_v && P.s_v) P.s_v[offx + (int64_t)k * NX + l * RX + a] = vo;  // work->v of this iteration
-                    }
-                    const T e1 = tabs(xo[a] - v), e2 = tabs(vo - v);
-                    rpx = (e1 > rpx) ? e1 : rpx;
-                    rdx = (e2 > rdx) ? e2 : rdx;
+                    gn_[a] = (more && xv[a]) ? sG[(k + 1) * SX + a * 32] : T(0);
+                    vn_[a] = (more && xv[a]) ? sV[(k + 1) * SX + a * 32] : T(0);
                 }
-                if (k < N - 1) {
-                    T u[RU], Uf[NU];
 #pragma unroll
-                    for (int b = 0; b < RU; ++b) {
-                        const T d = uv[b] ? sD[iu(k, b)] : T(0);
+                for (int b = 0; b < RU; ++b) {
+                    yn_[b] = (moreu && uv[b]) ? sY[(k + 1) * SU + b * 32] : T(0);
+                    zn_[b] = (moreu && uv[b]) ? sZ[(k + 1) * SU + b * 32] : T(0);
+                    dn_[b] = (moreu && uv[b]) ? sD[(k + 1) * SU + b * 32] : T(0);
+                }
+                if (tvb) {
+#pragma unroll
+                    for (int a = 0; a < RX; ++a) {
+                        loX[a] = (enx && xv[a]) ? __ldg(P.x_min + (int64_t)k * NX + l * RX + a) : T(0);
+                        hiX[a] = (enx && xv[a]) ? __ldg(P.x_max + (int64_t)k * NX + l * RX + a) : T(0);
+                    }
+                    if (k < N - 1) {
+#pragma unroll
+                        for (int b = 0; b < RU; ++b) {
+                            loU[b] = (enu && uv[b]) ? __ldg(P.u_min + (int64_t)k * NU + l * RU + b) : T(0);
+                            hiU[b] = (enu && uv[b]) ? __ldg(P.u_max + (int64_t)k * NU + l * RU + b) : T(0);
+                        }
+                    }
+                }
+                T u[RU], Uf[NU];
+                if (k < N - 1) {
+#pragma unroll
+                    for (int b = 0; b < RU; ++b) {  // u_k = -(Kinf x_k) - d_k
                         T t = mK[b][0] * Xf[0];
 #pragma unroll
                         for (int m = 1; m < NX; ++m) t = mac<FAST>(t, mK[b][m], Xf[m]);
-                        u[b] = (-t) - d;
+                        u[b] = (-t) - dc[b];
                     }
                     gather<T, RU, L, NU>(u, Uf);
+                }
+                // state column k: vnew = clamp(x + g), g += x - vnew
+#pragma unroll
+                for (int a = 0; a < RX; ++a) {
+                    T vo = vc[a];
+                    if constexpr (SLOW) {
+                        if (vin) vo = (P.s_v && xv[a]) ? P.s_v[offx + (int64_t)k * NX + l * RX + a] : T(0);
+                    }
+                    T v = xo[a] + gc[a];
+                    if (enx) v = clamp_box<FAST>(v, loX[a], hiX[a]);
+                    const T gnew = (gc[a] + xo[a]) - v;
+                    if (active && xv[a]) {
+                        sV[k * SX + a * 32] = v;
+                        sG[k * SX + a * 32] = gnew;
+                        if constexpr (SLOW) {
+                            if (P.s_v) P.s_v[offx + (int64_t)k * NX + l * RX + a] = vo;  // work->v of this iteration
+                        }
+                    }
+                    rpx = absmax(rpx, xo[a] - v);
+                    rdx = absmax(rdx, vo - v);
+                }
+                if (k < N - 1) {
 #pragma unroll
                     for (int b = 0; b < RU; ++b) {
-                        const T y = (zin || !uv[b]) ? T(0) : sY[iu(k, b)];
-                        T zo;
-                        if (vin) zo = (P.s_z && uv[b]) ? P.s_z[offu + (int64_t)k * NU + l * RU + b] : T(0);
-                        else zo = (zin || !uv[b]) ? T(0) : sZ[iu(k, b)];
-                        T z = u[b] + y;
-                        if (P.en_input_bound) {
-                            const T lo = tvb ? (uv[b] ? __ldg(P.u_min + (int64_t)k * NU + l * RU + b) : T(0)) : loU[b];
-                            const T hi = tvb ? (uv[b] ? __ldg(P.u_max + (int64_t)k * NU + l * RU + b) : T(0)) : hiU[b];
-                            z = clamp_ref(z, lo, hi);
+                        T zo = zc[b];
+                        if constexpr (SLOW) {
+                            if (vin) zo = (P.s_z && uv[b]) ? P.s_z[offu + (int64_t)k * NU + l * RU + b] : T(0);
                         }
-                        const T yn = (y + u[b]) - z;
+                        T z = u[b] + yc[b];
+                        if (enu) z = clamp_box<FAST>(z, loU[b], hiU[b]);
+                        const T ynew = (yc[b] + u[b]) - z;
                         if (active && uv[b]) {
-                            sZ[iu(k, b)] = z;
-                            sY[iu(k, b)] = yn;
-                            if (keep_v && P.s_z) P.s_z[offu + (int64_t)k * NU + l * RU + b] = zo;
+                            sZ[k * SU + b * 32] = z;
+                            sY[k * SU + b * 32] = ynew;
+                            if constexpr (SLOW) {
+                                if (P.s_z) P.s_z[offu + (int64_t)k * NU + l * RU + b] = zo;
+                            }
                         }
-                        const T e1 = tabs(u[b] - z), e2 = tabs(zo - z);
-                        rpu = (e1 > rpu) ? e1 : rpu;
-                        rdu = (e2 > rdu) ? e2 : rdu;
+                        rpu = absmax(rpu, u[b] - z);
+                        rdu = absmax(rdu, zo - z);
                     }
                     // x_{k+1} = (A x_k + B u_k) + f
 #pragma unroll
@@ -382,7 +387,85 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
                     }
                     gather<T, RX, L, NX>(xo, Xf);
                 }
+#pragma unroll
+                for (int a = 0; a < RX; ++a) {
+                    gc[a] = gn_[a];
+                    vc[a] = vn_[a];
+                }
+#pragma unroll
+                for (int b = 0; b < RU; ++b) {
+                    yc[b] = yn_[b];
+                    zc[b] = zn_[b];
+                    dc[b] = dn_[b];
+                }
             }
+        };
+
+        for (int it = 0; it < P.max_iter; ++it) {
+            if (!__any_sync(0xffffffffu, active)) break;
+
+            // ---- terminal cost + backward pass (update_linear_cost fused, software-pipelined by one column) ----
+            T po[RX], Pf[NX];
+#pragma unroll
+            for (int a = 0; a < RX; ++a) {
+                const T vn = xv[a] ? sV[(N - 1) * SX + a * 32] : T(0), g = xv[a] ? sG[(N - 1) * SX + a * 32] : T(0);
+                po[a] = nmac<FAST>(pterm[a], rho, vn - g);
+            }
+            gather<T, RX, L, NX>(po, Pf);
+            T q[RX], r[RU], Rf[NU];
+            cost_x(N - 2, q);
+            cost_u(N - 2, r);
+            gather<T, RU, L, NU>(r, Rf);
+            for (int k = N - 2; k >= 0; --k) {
+                // next column's cost (independent of p): overlaps with the dot-product chains below
+                T qn[RX], rn[RU], Rn[NU];
+                if (k > 0) {
+                    cost_x(k - 1, qn);
+                    cost_u(k - 1, rn);
+                    gather<T, RU, L, NU>(rn, Rn);
+                }
+                // d_k = Quu_inv ((B^T p_{k+1} + r_k) + BPf)
+                T s[RU], Sf[NU];
+#pragma unroll
+                for (int b = 0; b < RU; ++b) {
+                    T t = mBt[b][0] * Pf[0];
+#pragma unroll
+                    for (int m = 1; m < NX; ++m) t = mac<FAST>(t, mBt[b][m], Pf[m]);
+                    s[b] = (t + r[b]) + vBPf[b];
+                }
+                gather<T, RU, L, NU>(s, Sf);
+                // p_k = ((q_k + AmBKt p_{k+1}) - Kinf^T r_k) + APf
+#pragma unroll
+                for (int a = 0; a < RX; ++a) {
+                    T acc = mAmBKt[a][0] * Pf[0];
+#pragma unroll
+                    for (int m = 1; m < NX; ++m) acc = mac<FAST>(acc, mAmBKt[a][m], Pf[m]);
+                    T kr = mKt[a][0] * Rf[0];
+#pragma unroll
+                    for (int j = 1; j < NU; ++j) kr = mac<FAST>(kr, mKt[a][j], Rf[j]);
+                    po[a] = ((q[a] + acc) - kr) + vAPf[a];
+                }
+                gather<T, RX, L, NX>(po, Pf);
+#pragma unroll
+                for (int b = 0; b < RU; ++b) {
+                    T t = mQuu[b][0] * Sf[0];
+#pragma unroll
+                    for (int m = 1; m < NU; ++m) t = mac<FAST>(t, mQuu[b][m], Sf[m]);
+                    if (active && uv[b]) sD[k * SU + b * 32] = t;
+                }
+#pragma unroll
+                for (int a = 0; a < RX; ++a) q[a] = qn[a];
+#pragma unroll
+                for (int b = 0; b < RU; ++b) r[b] = rn[b];
+#pragma unroll
+                for (int j = 0; j < NU; ++j) Rf[j] = Rn[j];
+            }
+            __syncwarp();
+
+            T rpx = T(0), rdx = T(0), rpu = T(0), rdu = T(0);
+            const bool vin = (!cold) && it == 0;
+            if (vin || keep_v) forward(BoolTag<true>{}, vin, rpx, rdx, rpu, rdu);
+            else forward(BoolTag<false>{}, false, rpx, rdx, rpu, rdu);
             __syncwarp();
             // ---- termination_condition (admm.cpp:310-328), per instance ----
             rpx = group_max<T, L>(rpx);
@@ -413,40 +496,38 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
                 r[0] = res_px; r[1] = res_dx; r[2] = res_pu; r[3] = res_du;
             }
         }
-        // when no iteration ran on a cold start the shared-memory state was never written: define it as zero
-        if (cold && P.max_iter <= 0) {
-            for (size_t w = lane; w < warp_elems; w += 32) wbase[w] = T(0);
-        }
         __syncwarp();
         // solution->x = vnew, solution->u = znew; work->vnew/znew/g/y; coalesced transposing copy per instance
-        for (int s = 0; s < IPW; ++s) {
-            const int64_t ib = (int64_t)grp * IPW + s;
-            if (ib >= P.B) break;
-            const int64_t ox = ib * (int64_t)N * NX, ou = ib * (int64_t)(N - 1) * NU;
-            // per-instance flags live in the lanes of slot s
-            const int s_solved = __shfl_sync(0xffffffffu, solved, s * L);
-            const int s_it = __shfl_sync(0xffffffffu, it_done, s * L);
-            for (int e = lane; e < N * NX; e += 32) {
-                const int k = e / NX, i = e - k * NX;
-                const size_t w = ((size_t)k * RX + (i % RX)) * 32 + s * L + i / RX;
-                const T v = sV[w];
-                P.sol_x[ox + e] = v;
-                if (P.s_vnew) P.s_vnew[ox + e] = v;
-                if (P.s_g) P.s_g[ox + e] = sG[w];
-                // work->v: previous vnew if the solve converged (already streamed out during the last forward
-                // pass), else = vnew (admm.cpp:445); untouched when no iteration ran
-                if (P.s_v && !s_solved && s_it > 0) P.s_v[ox + e] = v;
-                else if (P.s_v && cold && s_it == 0) P.s_v[ox + e] = T(0);
-            }
-            for (int e = lane; e < (N - 1) * NU; e += 32) {
-                const int k = e / NU, j = e - k * NU;
-                const size_t w = ((size_t)k * RU + (j % RU)) * 32 + s * L + j / RU;
-                const T z = sZ[w];
-                P.sol_u[ou + e] = z;
-                if (P.s_znew) P.s_znew[ou + e] = z;
-                if (P.s_y) P.s_y[ou + e] = sY[w];
-                if (P.s_z && !s_solved && s_it > 0) P.s_z[ou + e] = z;
-                else if (P.s_z && cold && s_it == 0) P.s_z[ou + e] = T(0);
+        {
+            const T *uV = wbase, *uG = uV + N * SX, *uZ = uG + N * SX, *uY = uZ + (N - 1) * SU;
+            for (int s = 0; s < IPW; ++s) {
+                const int64_t ib = (int64_t)grp * IPW + s;
+                if (ib >= P.B) break;
+                const int64_t ox = ib * (int64_t)N * NX, ou = ib * (int64_t)(N - 1) * NU;
+                const int s_solved = __shfl_sync(0xffffffffu, solved, s * L);
+                const int s_it = __shfl_sync(0xffffffffu, it_done, s * L);
+                for (int e = lane; e < N * NX; e += 32) {
+                    const int k = e / NX, i = e - k * NX;
+                    const int w = (k * RX + (i % RX)) * 32 + s * L + i / RX;
+                    const T v = uV[w];
+                    P.sol_x[ox + e] = v;
+                    if (P.s_vnew) P.s_vnew[ox + e] = v;
+                    if (P.s_g) P.s_g[ox + e] = uG[w];
+                    // work->v: previous vnew if the solve converged (streamed out during the last forward pass),
+                    // else = vnew (admm.cpp:445); untouched when no iteration ran on a warm start
+                    if (P.s_v && !s_solved && s_it > 0) P.s_v[ox + e] = v;
+                    else if (P.s_v && cold && s_it == 0) P.s_v[ox + e] = T(0);
+                }
+                for (int e = lane; e < (N - 1) * NU; e += 32) {
+                    const int k = e / NU, j = e - k * NU;
+                    const int w = (k * RU + (j % RU)) * 32 + s * L + j / RU;
+                    const T z = uZ[w];
+                    P.sol_u[ou + e] = z;
+                    if (P.s_znew) P.s_znew[ou + e] = z;
+                    if (P.s_y) P.s_y[ou + e] = uY[w];
+                    if (P.s_z && !s_solved && s_it > 0) P.s_z[ou + e] = z;
+                    else if (P.s_z && cold && s_it == 0) P.s_z[ou + e] = T(0);
+                }
             }
         }
         // work->x / work->u: replay the last rollout from d and x0 (bit-identical to the last forward pass),
@@ -457,21 +538,20 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
 #pragma unroll
             for (int a = 0; a < RX; ++a) xo[a] = x0o[a];
             gather<T, RX, L, NX>(xo, Xf);
-            const bool ran = it_done > 0;
             for (int k = 0; k < N; ++k) {
 #pragma unroll
                 for (int a = 0; a < RX; ++a)
-                    if (xv[a]) sV[ix(k, a)] = xo[a];
+                    if (xv[a]) sV[k * SX + a * 32] = xo[a];
                 if (k < N - 1) {
                     T u[RU], Uf[NU];
 #pragma unroll
                     for (int b = 0; b < RU; ++b) {
-                        const T d = uv[b] ? sD[iu(k, b)] : T(0);
+                        const T d = uv[b] ? sD[k * SU + b * 32] : T(0);
                         T t = mK[b][0] * Xf[0];
 #pragma unroll
                         for (int m = 1; m < NX; ++m) t = mac<FAST>(t, mK[b][m], Xf[m]);
                         u[b] = (-t) - d;
-                        if (uv[b]) sZ[iu(k, b)] = u[b];
+                        if (uv[b]) sZ[k * SU + b * 32] = u[b];
                     }
                     gather<T, RU, L, NU>(u, Uf);
 #pragma unroll
@@ -487,8 +567,8 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
                     gather<T, RX, L, NX>(xo, Xf);
                 }
             }
-            (void)ran;
             __syncwarp();
+            const T *uV = wbase, *uZ = uV + 2 * N * SX;
             for (int s = 0; s < IPW; ++s) {
                 const int64_t ib = (int64_t)grp * IPW + s;
                 if (ib >= P.B) break;
@@ -497,15 +577,15 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
                 if (P.s_x)
                     for (int e = lane; e < N * NX; e += 32) {
                         const int k = e / NX, i = e - k * NX;
-                        const size_t w = ((size_t)k * RX + (i % RX)) * 32 + s * L + i / RX;
-                        if (s_it > 0 || k == 0) P.s_x[ox + e] = sV[w];
+                        const int w = (k * RX + (i % RX)) * 32 + s * L + i / RX;
+                        if (s_it > 0 || k == 0) P.s_x[ox + e] = uV[w];
                         else if (cold) P.s_x[ox + e] = T(0);
                     }
                 if (P.s_u)
                     for (int e = lane; e < (N - 1) * NU; e += 32) {
                         const int k = e / NU, j = e - k * NU;
-                        const size_t w = ((size_t)k * RU + (j % RU)) * 32 + s * L + j / RU;
-                        if (s_it > 0) P.s_u[ou + e] = sZ[w];
+                        const int w = (k * RU + (j % RU)) * 32 + s * L + j / RU;
+                        if (s_it > 0) P.s_u[ou + e] = uZ[w];
                         else if (cold) P.s_u[ou + e] = T(0);
                     }
             }

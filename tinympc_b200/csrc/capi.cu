@@ -92,6 +92,7 @@ struct tinympc_b200_solver {
     int device = 0;
     int sm_count = 0;
     int max_smem_optin = 0;
+    int l2_bytes = 0;
     int nx = 0, nu = 0, N = 0, dtype = 0;
     double rho = 0;
     const tmpc::DimEntry *dim = nullptr;
@@ -232,6 +233,40 @@ void base_desc(const tinympc_b200_solver *s, tmpc::LaunchDesc &d, const Features
     d.max_smem_optin = s->max_smem_optin;
 }
 
+// view of a (device) batch restricted to instances [b0, b0+nb)
+tinympc_batch_t slice_batch(const tinympc_b200_solver *s, const tinympc_batch_t &io, int64_t b0, int64_t nb) {
+    const size_t es = esize(s->dtype);
+    const size_t bx = es * s->nx * s->N, bu = es * s->nu * (s->N - 1);
+    tinympc_batch_t o = io;
+    o.B = nb;
+    auto adv = [&](const void *p, size_t per) -> void * { return p ? (void *)((const char *)p + per * (size_t)b0) : nullptr; };
+    o.x0 = adv(io.x0, es * s->nx);
+    if (io.xref_per_instance) o.Xref = adv(io.Xref, bx);
+    if (io.uref_per_instance) o.Uref = adv(io.Uref, bu);
+    void *const *sp = (void *const *)&io.state;
+    void **dp = (void **)&o.state;
+    const int nfields = sizeof(tinympc_state_t) / sizeof(void *);
+    for (int i = 0; i < nfields; ++i) dp[i] = adv(sp[i], (i % 2) == 0 ? bx : bu);
+    o.sol_x = adv(io.sol_x, bx);
+    o.sol_u = adv(io.sol_u, bu);
+    o.iter = (int32_t *)adv(io.iter, sizeof(int32_t));
+    o.solved = (int32_t *)adv(io.solved, sizeof(int32_t));
+    o.residuals = adv(io.residuals, 4 * es);
+    return o;
+}
+
+// TPI streams its per-instance state through global memory every iteration.  TINYMPC_TPI_CHUNK=<n> solves
+// the batch in sub-batches of n instances (an experiment knob: an L2-sized working set did NOT pay off).
+int64_t tpi_chunk_instances(const tinympc_b200_solver *s, const Features &ft, int64_t B) {
+    if (const char *e = std::getenv("TINYMPC_TPI_CHUNK")) {
+        long long v = std::atoll(e);
+        if (v > 0) return std::min<int64_t>(B, (v + 127) / 128 * 128);
+        if (v < 0) return B;  // chunking off
+    }
+    (void)ft;
+    return B;  // measured on B200 (profiles/r01_tpi_chunk_sweep.txt): sub-batching only lowers occupancy; TPI is latency-, not L2-, limited
+}
+
 // enqueue one batched solve on `stream` (device pointers); fills stats
 int enqueue(tinympc_b200_solver *s, const tinympc_batch_t *io, cudaStream_t stream, bool timed) {
     if (int rc = check_ready(s)) return rc;
@@ -244,27 +279,33 @@ int enqueue(tinympc_b200_solver *s, const tinympc_batch_t *io, cudaStream_t stre
     tmpc::LaunchDesc d;
     base_desc(s, d, ft);
     d.family = family;
-    d.io = *io;
     d.stream = stream;
-    if (int rc = setup_workspace(s, d, ft, io->B, family)) return rc;
+    const int64_t chunk = family == TINYMPC_KERNEL_TPI ? tpi_chunk_instances(s, ft, io->B) : io->B;
+    if (int rc = setup_workspace(s, d, ft, chunk, family)) return rc;
     if (family == TINYMPC_KERNEL_GPI) {
         if (s->queue.ensure(256)) return fail(TINYMPC_ERR_CUDA, "queue allocation failed");
         CUDA_TRY(cudaMemsetAsync(s->queue.p, 0, 256, stream));
         d.work_queue = s->queue.p;
     }
     if (timed) CUDA_TRY(cudaEventRecord(s->ev0, stream));
-    int rc = s->dim->launch(&d);
-    if (rc == TINYMPC_ERR_CUDA) return fail(rc, std::string("kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
-    if (rc) return fail(rc, "no compiled kernel for this (dtype, mode, family) combination");
+    int64_t launches = 0, ctas = 0;
+    for (int64_t b0 = 0; b0 < io->B; b0 += chunk) {
+        d.io = slice_batch(s, *io, b0, std::min<int64_t>(chunk, io->B - b0));
+        int rc = s->dim->launch(&d);
+        if (rc == TINYMPC_ERR_CUDA) return fail(rc, std::string("kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+        if (rc) return fail(rc, "no compiled kernel for this (dtype, mode, family) combination");
+        ++launches;
+        ctas += d.out_ctas;
+    }
     if (timed) CUDA_TRY(cudaEventRecord(s->ev1, stream));
     s->timed = timed;
     s->stats.instances = io->B;
-    s->stats.kernel_launches = 1;
+    s->stats.kernel_launches = launches;
     s->stats.kernel_family = family;
     s->stats.lanes_per_instance = d.out_lanes_per_instance;
     s->stats.instances_per_cta = d.out_instances_per_cta;
     s->stats.smem_bytes_per_cta = d.out_smem;
-    s->stats.ctas = d.out_ctas;
+    s->stats.ctas = (int)ctas;
     s->stats.threads_per_cta = d.out_threads;
     return TINYMPC_OK;
 }
@@ -345,6 +386,7 @@ int tinympc_b200_create(const tinympc_problem_t *p, int32_t device, tinympc_b200
     s->device = device;
     s->sm_count = prop.multiProcessorCount;
     s->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    s->l2_bytes = prop.l2CacheSize;
     s->nx = p->nx; s->nu = p->nu; s->N = p->N; s->dtype = p->dtype; s->rho = p->rho;
     s->dim = dim;
     const size_t es = esize(p->dtype), nx = p->nx, nu = p->nu, N = p->N;
@@ -629,7 +671,7 @@ int tinympc_b200_solve_host(tinympc_b200_solver_t *s, const tinympc_batch_t *io)
         CUDA_TRY(cudaEventRecord(s->ev_in[slot], s->st_h2d));
         CUDA_TRY(cudaStreamWaitEvent(s->st_k, s->ev_in[slot], 0));
         if (int rc = enqueue(s, &d, s->st_k, false)) return rc;
-        ++launches;
+        launches += s->stats.kernel_launches;
         CUDA_TRY(cudaEventRecord(s->ev_k[slot], s->st_k));
         CUDA_TRY(cudaStreamWaitEvent(s->st_d2h, s->ev_k[slot], 0));
         {

@@ -63,6 +63,21 @@ __device__ __forceinline__ T group_max(T v) {
 
 constexpr int GPI_MAX_WARPS = 8;
 
+// Shared-memory accessors on 32-bit shared-window addresses: keeps the generic->shared conversion
+// (S2UR SR_CgaCtaId + ULEA) and 64-bit address arithmetic out of the hot loops.
+__device__ __forceinline__ float lds(unsigned a, float) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ double lds(unsigned a, double) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts(unsigned a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts(unsigned a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+
 template <bool B>
 struct BoolTag {
     static constexpr bool value = B;
@@ -177,6 +192,20 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
     T *sY = sZ + (N - 1) * RU * 32;       // y
     T *sD = sY + (N - 1) * RU * 32;       // d
     constexpr int SX = RX * 32, SU = RU * 32;  // per-k strides
+    constexpr unsigned ES = (unsigned)sizeof(T);
+    const unsigned aV = (unsigned)__cvta_generic_to_shared(sV), aG = (unsigned)__cvta_generic_to_shared(sG),
+                   aZ = (unsigned)__cvta_generic_to_shared(sZ), aY = (unsigned)__cvta_generic_to_shared(sY),
+                   aD = (unsigned)__cvta_generic_to_shared(sD);
+    auto LV = [&](int k, int a) { return lds(aV + (unsigned)(k * SX + a * 32) * ES, T()); };
+    auto LG = [&](int k, int a) { return lds(aG + (unsigned)(k * SX + a * 32) * ES, T()); };
+    auto LZ = [&](int k, int b) { return lds(aZ + (unsigned)(k * SU + b * 32) * ES, T()); };
+    auto LY = [&](int k, int b) { return lds(aY + (unsigned)(k * SU + b * 32) * ES, T()); };
+    auto LD = [&](int k, int b) { return lds(aD + (unsigned)(k * SU + b * 32) * ES, T()); };
+    auto SV_ = [&](int k, int a, T v) { sts(aV + (unsigned)(k * SX + a * 32) * ES, v); };
+    auto SG_ = [&](int k, int a, T v) { sts(aG + (unsigned)(k * SX + a * 32) * ES, v); };
+    auto SZ_ = [&](int k, int b, T v) { sts(aZ + (unsigned)(k * SU + b * 32) * ES, v); };
+    auto SY_ = [&](int k, int b, T v) { sts(aY + (unsigned)(k * SU + b * 32) * ES, v); };
+    auto SD_ = [&](int k, int b, T v) { sts(aD + (unsigned)(k * SU + b * 32) * ES, v); };
 
     const bool cold = P.cold != 0;
     const int64_t ngroups = (P.B + IPW - 1) / IPW;
@@ -257,19 +286,19 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
         T res_px = T(0), res_dx = T(0), res_pu = T(0), res_du = T(0);
 
         // linear cost of column k for this lane's rows: q = -(xref*Qd) - rho*(vnew - g), r = -(uref*Rd) - rho*(znew - y)
-        auto cost_x = [&](int k, T (&q)[RX]) {
+        auto cost_x = [&](int k, const T *xp, T (&q)[RX]) {  // xp -> this lane's rows of Xref column k
 #pragma unroll
             for (int a = 0; a < RX; ++a) {
-                const T xr = xv[a] ? __ldg(xrefp + (int64_t)k * NX + a) : T(0);
-                const T vn = xv[a] ? sV[k * SX + a * 32] : T(0), g = xv[a] ? sG[k * SX + a * 32] : T(0);
+                const T xr = xv[a] ? __ldg(xp + a) : T(0);
+                const T vn = xv[a] ? LV(k, a) : T(0), g = xv[a] ? LG(k, a) : T(0);
                 q[a] = nmac<FAST>(-(xr * vQd[a]), rho, vn - g);
             }
         };
-        auto cost_u = [&](int k, T (&r)[RU]) {
+        auto cost_u = [&](int k, const T *up, T (&r)[RU]) {
 #pragma unroll
             for (int b = 0; b < RU; ++b) {
-                const T ur = (urefp && uv[b]) ? __ldg(urefp + (int64_t)k * NU + b) : T(0);
-                const T zn = uv[b] ? sZ[k * SU + b * 32] : T(0), y = uv[b] ? sY[k * SU + b * 32] : T(0);
+                const T ur = (up && uv[b]) ? __ldg(up + b) : T(0);
+                const T zn = uv[b] ? LZ(k, b) : T(0), y = uv[b] ? LY(k, b) : T(0);
                 r[b] = nmac<FAST>(-(ur * vRd[b]), rho, zn - y);
             }
         };
@@ -285,29 +314,29 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
             T gc[RX], vc[RX], yc[RU], zc[RU], dc[RU];  // state of the current column (prefetched)
 #pragma unroll
             for (int a = 0; a < RX; ++a) {
-                gc[a] = xv[a] ? sG[a * 32] : T(0);
-                vc[a] = xv[a] ? sV[a * 32] : T(0);
+                gc[a] = xv[a] ? LG(0, a) : T(0);
+                vc[a] = xv[a] ? LV(0, a) : T(0);
             }
 #pragma unroll
             for (int b = 0; b < RU; ++b) {
-                yc[b] = uv[b] ? sY[b * 32] : T(0);
-                zc[b] = uv[b] ? sZ[b * 32] : T(0);
-                dc[b] = uv[b] ? sD[b * 32] : T(0);
+                yc[b] = uv[b] ? LY(0, b) : T(0);
+                zc[b] = uv[b] ? LZ(0, b) : T(0);
+                dc[b] = uv[b] ? LD(0, b) : T(0);
             }
             for (int k = 0; k < N; ++k) {
                 // prefetch the next column's state while this one is being processed
                 T gn_[RX], vn_[RX], yn_[RU], zn_[RU], dn_[RU];
-                const bool more = k + 1 < N, moreu = k + 2 < N;
+                const int kx = (k + 1 < N) ? k + 1 : k, ku = (k + 2 < N) ? k + 1 : ((N >= 2) ? N - 2 : 0);  // clamped: always valid
 #pragma unroll
                 for (int a = 0; a < RX; ++a) {
-                    gn_[a] = (more && xv[a]) ? sG[(k + 1) * SX + a * 32] : T(0);
-                    vn_[a] = (more && xv[a]) ? sV[(k + 1) * SX + a * 32] : T(0);
+                    gn_[a] = xv[a] ? LG(kx, a) : T(0);
+                    vn_[a] = xv[a] ? LV(kx, a) : T(0);
                 }
 #pragma unroll
                 for (int b = 0; b < RU; ++b) {
-                    yn_[b] = (moreu && uv[b]) ? sY[(k + 1) * SU + b * 32] : T(0);
-                    zn_[b] = (moreu && uv[b]) ? sZ[(k + 1) * SU + b * 32] : T(0);
-                    dn_[b] = (moreu && uv[b]) ? sD[(k + 1) * SU + b * 32] : T(0);
+                    yn_[b] = uv[b] ? LY(ku, b) : T(0);
+                    zn_[b] = uv[b] ? LZ(ku, b) : T(0);
+                    dn_[b] = uv[b] ? LD(ku, b) : T(0);
                 }
                 if (tvb) {
 #pragma unroll
@@ -345,8 +374,8 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
                     if (enx) v = clamp_box<FAST>(v, loX[a], hiX[a]);
                     const T gnew = (gc[a] + xo[a]) - v;
                     if (active && xv[a]) {
-                        sV[k * SX + a * 32] = v;
-                        sG[k * SX + a * 32] = gnew;
+                        SV_(k, a, v);
+                        SG_(k, a, gnew);
                         if constexpr (SLOW) {
                             if (P.s_v) P.s_v[offx + (int64_t)k * NX + l * RX + a] = vo;  // work->v of this iteration
                         }
@@ -365,8 +394,8 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
                         if (enu) z = clamp_box<FAST>(z, loU[b], hiU[b]);
                         const T ynew = (yc[b] + u[b]) - z;
                         if (active && uv[b]) {
-                            sZ[k * SU + b * 32] = z;
-                            sY[k * SU + b * 32] = ynew;
+                            SZ_(k, b, z);
+                            SY_(k, b, ynew);
                             if constexpr (SLOW) {
                                 if (P.s_z) P.s_z[offu + (int64_t)k * NU + l * RU + b] = zo;
                             }
@@ -408,20 +437,24 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
             T po[RX], Pf[NX];
 #pragma unroll
             for (int a = 0; a < RX; ++a) {
-                const T vn = xv[a] ? sV[(N - 1) * SX + a * 32] : T(0), g = xv[a] ? sG[(N - 1) * SX + a * 32] : T(0);
+                const T vn = xv[a] ? LV(N - 1, a) : T(0), g = xv[a] ? LG(N - 1, a) : T(0);
                 po[a] = nmac<FAST>(pterm[a], rho, vn - g);
             }
             gather<T, RX, L, NX>(po, Pf);
             T q[RX], r[RU], Rf[NU];
-            cost_x(N - 2, q);
-            cost_u(N - 2, r);
+            const T *xp = xrefp + (int64_t)(N - 2) * NX;
+            const T *up = urefp ? urefp + (int64_t)(N - 2) * NU : nullptr;
+            cost_x(N - 2, xp, q);
+            cost_u(N - 2, up, r);
             gather<T, RU, L, NU>(r, Rf);
             for (int k = N - 2; k >= 0; --k) {
                 // next column's cost (independent of p): overlaps with the dot-product chains below
                 T qn[RX], rn[RU], Rn[NU];
                 if (k > 0) {
-                    cost_x(k - 1, qn);
-                    cost_u(k - 1, rn);
+                    xp -= NX;
+                    if (up) up -= NU;
+                    cost_x(k - 1, xp, qn);
+                    cost_u(k - 1, up, rn);
                     gather<T, RU, L, NU>(rn, Rn);
                 }
                 // d_k = Quu_inv ((B^T p_{k+1} + r_k) + BPf)
@@ -451,7 +484,7 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
                     T t = mQuu[b][0] * Sf[0];
 #pragma unroll
                     for (int m = 1; m < NU; ++m) t = mac<FAST>(t, mQuu[b][m], Sf[m]);
-                    if (active && uv[b]) sD[k * SU + b * 32] = t;
+                    if (active && uv[b]) SD_(k, b, t);
                 }
 #pragma unroll
                 for (int a = 0; a < RX; ++a) q[a] = qn[a];
@@ -541,17 +574,17 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
             for (int k = 0; k < N; ++k) {
 #pragma unroll
                 for (int a = 0; a < RX; ++a)
-                    if (xv[a]) sV[k * SX + a * 32] = xo[a];
+                    if (xv[a]) SV_(k, a, xo[a]);
                 if (k < N - 1) {
                     T u[RU], Uf[NU];
 #pragma unroll
                     for (int b = 0; b < RU; ++b) {
-                        const T d = uv[b] ? sD[k * SU + b * 32] : T(0);
+                        const T d = uv[b] ? LD(k, b) : T(0);
                         T t = mK[b][0] * Xf[0];
 #pragma unroll
                         for (int m = 1; m < NX; ++m) t = mac<FAST>(t, mK[b][m], Xf[m]);
                         u[b] = (-t) - d;
-                        if (uv[b]) sZ[k * SU + b * 32] = u[b];
+                        if (uv[b]) SZ_(k, b, u[b]);
                     }
                     gather<T, RU, L, NU>(u, Uf);
 #pragma unroll

@@ -155,7 +155,7 @@ __device__ __forceinline__ void soc_cols(T (&v)[NE], int ncones, const int *star
 constexpr int TPI_THREADS = 128;
 
 template <typename T, int NX, int NU, bool FAST, bool EXT>
-__global__ void __launch_bounds__(TPI_THREADS) tpi_solve_kernel(const __grid_constant__ KParams<T, NX, NU> P) {
+__global__ void __launch_bounds__(TPI_THREADS, (sizeof(T) == 4 && !EXT) ? 4 : 2) tpi_solve_kernel(const __grid_constant__ KParams<T, NX, NU> P) {
     using SX = SoA<T, NX>;
     using SU = SoA<T, NU>;
     const int N = P.N;

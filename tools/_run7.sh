@@ -1,0 +1,1 @@
+python -m pytest tests/test_gpu_shim.py -x -q 2>&1 | tail -15

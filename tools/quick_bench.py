@@ -47,7 +47,7 @@ for r in range(a.reps + 2):
     ms.append(s.stats()["kernel_ms"])
 st = s.stats()
 iters = int(out["iter"].sum().item())
-best = min(ms[2:])
+best = min(ms[2:] or ms)
 print(f"{a.config} kernel={a.kernel}->{st['kernel_family']} mode={a.mode} B={B} iters={iters} solved={int(out['solved'].sum().item())} "
       f"ms(all)={[round(m, 3) for m in ms]} best={best:.3f} ms  -> {B / best * 1e3:.3e} inst/s  {iters / best * 1e3:.3e} ADMM it/s "
       f"ctas={st['ctas']} thr={st['threads_per_cta']} smem={st['smem_bytes_per_cta']} L={st['lanes_per_instance']}")

@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default="strict", choices=["strict", "fast"])
-    ap.add_argument("--kernel", default="auto", choices=["auto", "tpi", "gpi"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "tpi", "gpi", "hybrid"])
     ap.add_argument("--cpu-sample", type=int, default=16384, help="instances in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
@@ -209,7 +209,7 @@ def main():
     dt = np.float32
     prob = setup_problem(spec, dt)
     mode = abi.MODE_STRICT if args.mode == "strict" else abi.MODE_FAST
-    kern = dict(auto=abi.KERNEL_AUTO, tpi=abi.KERNEL_TPI, gpi=abi.KERNEL_GPI)[args.kernel]
+    kern = dict(auto=abi.KERNEL_AUTO, tpi=abi.KERNEL_TPI, gpi=abi.KERNEL_GPI, hybrid=abi.KERNEL_HYBRID)[args.kernel]
     solver = BatchedTinySolver(prob, spec.settings, device=local, mode=mode, kernel=kern)
     inst = wl.hovering_instances(B, N=N_HORIZON, dtype=dt)
 
@@ -312,10 +312,10 @@ def main():
         "metric": METRIC, "value": world * B * K / (red["ms"] * 1e-3), "unit": "instances/s", "n_gpus": world, "steps": K,
         "warmup": W, "ms_per_step": red["ms"] / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "mode": args.mode, "kernel": {1: "tpi", 2: "gpi"}[st["kernel_family"]],
+        "config": {"workload": WORKLOAD, "mode": args.mode, "kernel": {1: "tpi", 2: "gpi", 3: "hybrid(gpi+tpi co-resident)"}[st["kernel_family"]],
                    "l2": "flushed (256 MiB write) between timed steps", "parallelism": f"batch-sharded x{world}, no data-path collective",
                    "lanes_per_instance": st["lanes_per_instance"], "ctas": st["ctas"], "threads_per_cta": st["threads_per_cta"],
-                   "smem_bytes_per_cta": st["smem_bytes_per_cta"]},
+                   "smem_bytes_per_cta": st["smem_bytes_per_cta"], "gpi_instances": st["gpi_instances"]},
         "admm_iters_per_s_per_gpu": red["iters"] / world / (red["ms"] * 1e-3),
         "solved_fraction": red["solved"] / red["instances"],
         "residual_max": red["res_max"],

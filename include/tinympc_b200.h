@@ -46,6 +46,7 @@ extern "C" {
 #define TINYMPC_KERNEL_AUTO 0
 #define TINYMPC_KERNEL_TPI 1 /* thread-per-instance, state streamed through HBM/L2 (any feature set)   */
 #define TINYMPC_KERNEL_GPI 2 /* lane-group-per-instance, state resident in shared memory (box only)    */
+#define TINYMPC_KERNEL_HYBRID 3 /* GPI and TPI co-resident on every SM, batch split between them        */
 
 /* error codes */
 #define TINYMPC_OK 0
@@ -176,6 +177,7 @@ typedef struct tinympc_b200_stats {
     int32_t smem_bytes_per_cta;
     int32_t ctas;
     int32_t threads_per_cta;
+    int64_t gpi_instances; /* HYBRID: how many instances of the batch the GPI kernel took (rest: TPI) */
 } tinympc_b200_stats_t;
 
 /* tiny_set_default_settings (tiny_api.cpp:413-441, tiny_api_constants.hpp:5-16) */
@@ -219,6 +221,14 @@ int tinympc_b200_solve(tinympc_b200_solver_t *s, const tinympc_batch_t *io, void
 int tinympc_b200_solve_host(tinympc_b200_solver_t *s, const tinympc_batch_t *io);
 
 int tinympc_b200_get_stats(const tinympc_b200_solver_t *s, tinympc_b200_stats_t *stats);
+
+/*
+ * Closed-loop helper (the caller of the hot path, e.g. examples/quadrotor_tracking.cpp:105):
+ *     x0[b] <- (Adyn * x0[b] + Bdyn * u[b][:,0]) + fdyn        for b in [0, B)
+ * with x0 [B][nx] (in/out) and u = work->u [B][N-1][nu], all DEVICE pointers; ascending-k sums, no FMA.
+ * Lets thousands of simulated plants step without a host round trip between two tinympc_b200_solve calls.
+ */
+int tinympc_b200_advance(tinympc_b200_solver_t *s, int64_t B, void *x0, const void *u, void *cuda_stream);
 
 /* 1 if a kernel is compiled for (dtype,nx,nu); used by callers to fail early */
 int tinympc_b200_supported(int32_t dtype, int32_t nx, int32_t nu);

@@ -15,7 +15,7 @@ from tinympc_b200.solver import BatchedTinySolver, setup_problem
 
 pytestmark = pytest.mark.gpu
 
-KERNELS = {"tpi": abi.KERNEL_TPI, "gpi": abi.KERNEL_GPI}
+KERNELS = {"tpi": abi.KERNEL_TPI, "gpi": abi.KERNEL_GPI, "hybrid": abi.KERNEL_HYBRID, "auto": abi.KERNEL_AUTO}
 
 
 def _mk_solver(prob, st, kernel, mode=abi.MODE_STRICT):
@@ -177,7 +177,7 @@ def test_full_size_identical_instances_and_shard_invariance():
     B = 65536
     inst = wl.hovering_instances(B, N=50, dtype=dt)
     o = _port(prob, st, inst["x0"][:1], inst["Xref"], None, None, True, ("u",), nthreads=1)
-    for kernel in ("gpi", "tpi"):
+    for kernel in ("gpi", "tpi", "hybrid"):
         solver = _mk_solver(prob, st, kernel)
         g = solver.solve(inst["x0"], inst["Xref"], None, cold_start=True, want_state=("u",))
         for key in ("sol_x", "sol_u", "iter", "solved", "residuals", "u"):
@@ -197,9 +197,15 @@ def test_full_size_tracking_sample_vs_oracle():
     st = spec.settings
     B = 65536
     inst = wl.tracking_instances(B, N=50, seed=0, dtype=dt)
-    solver = _mk_solver(prob, st, "gpi")
-    g = solver.solve(inst["x0"], inst["Xref"], None, cold_start=True)
-    idx = np.arange(0, B, B // 512)
+    solver = _mk_solver(prob, st, "hybrid")  # GPI and TPI co-resident on every SM, batch split between them
+    batch, out = solver.make_device_batch(inst["x0"], inst["Xref"], None, cold_start=True)
+    solver.solve_device(batch)
+    import torch
+    torch.cuda.synchronize()
+    stt = solver.stats()
+    assert stt["kernel_family"] == abi.KERNEL_HYBRID and stt["kernel_launches"] == 2 and 0 < stt["gpi_instances"] < B
+    g = {k: v.cpu().numpy() for k, v in out.items() if v is not None}
+    idx = np.unique(np.concatenate([np.arange(0, B, B // 512), np.arange(stt["gpi_instances"] - 8, stt["gpi_instances"] + 8)]))
     o = _port(prob, st, inst["x0"][idx], inst["Xref"][idx], None, None, True, ())
     for key in H.OUT_KEYS:
         assert H.bits_equal(g[key][idx], o[key]), key
@@ -225,3 +231,44 @@ def test_errors_are_loud():
     with pytest.raises(TinyMPCError) as e:
         s2.solve(ri["x0"], ri["Xref"], ri["Uref"])
     assert e.value.code == abi.ERR_UNSUPPORTED
+
+
+@pytest.mark.parametrize("kernel", ["tpi", "gpi"])
+def test_device_resident_closed_loop_matches_oracle(kernel):
+    """the reference's closed loop (set x0 -> solve warm-started -> x0 = A x0 + B u0) for 300 plants kept
+    entirely on the GPU (DeviceMPCLoop + tinympc_b200_advance) equals the oracle stepping the same loop on the host."""
+    from tinympc_b200.closed_loop import DeviceMPCLoop
+
+    spec = wl.quadrotor(N=10)
+    dt = np.float32
+    prob = setup_problem(spec, dt)
+    st = spec.settings
+    B, steps = 300, 6
+    inst = wl.tracking_instances(B, N=10, seed=12, dtype=dt)
+    traj = inst["Xref"]
+    loop = DeviceMPCLoop(_mk_solver(prob, st, kernel), inst["x0"], reset_duals=True)
+    x0 = inst["x0"].copy()
+    state = None
+    A, Bm, f = prob.A, prob.B, prob.f
+    for k in range(steps):
+        Xref = np.ascontiguousarray(np.roll(traj, -k, axis=1))  # a different window every step
+        out = loop.step(Xref)
+        if state is not None:
+            state["g"] = np.zeros_like(state["g"])
+            state["y"] = np.zeros_like(state["y"])
+        o = _port(prob, st, x0, Xref, None, state, state is None, tuple(H.BOX_STATE))
+        for key in H.OUT_KEYS + H.BOX_STATE:
+            assert H.bits_equal(out[key].cpu().numpy(), o[key]), (k, key)
+        state = {n: o[n] for n in H.BOX_STATE}
+        u0 = o["u"][:, 0, :]
+        nxt = np.zeros_like(x0)
+        for i in range(prob.nx):  # same ascending-k, no-FMA arithmetic as tinympc_b200_advance
+            ax = A[i, 0] * x0[:, 0]
+            for m in range(1, prob.nx):
+                ax = ax + A[i, m] * x0[:, m]
+            bu = Bm[i, 0] * u0[:, 0]
+            for j in range(1, prob.nu):
+                bu = bu + Bm[i, j] * u0[:, j]
+            nxt[:, i] = (ax + bu) + f[i]
+        x0 = nxt
+        assert H.bits_equal(loop.x0.cpu().numpy(), x0), ("advance", k)

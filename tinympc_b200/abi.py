@@ -7,7 +7,7 @@ import ctypes as C
 
 F32, F64 = 0, 1
 MODE_STRICT, MODE_FAST = 0, 1
-KERNEL_AUTO, KERNEL_TPI, KERNEL_GPI = 0, 1, 2
+KERNEL_AUTO, KERNEL_TPI, KERNEL_GPI, KERNEL_HYBRID = 0, 1, 2, 3
 
 OK = 0
 ERR_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_NO_BOUNDS, ERR_CONE_DIM = -1, -2, -3, -4, -5
@@ -77,6 +77,7 @@ class Stats(C.Structure):
         ("kernel_family", C.c_int32), ("lanes_per_instance", C.c_int32),
         ("instances_per_cta", C.c_int32), ("smem_bytes_per_cta", C.c_int32),
         ("ctas", C.c_int32), ("threads_per_cta", C.c_int32),
+        ("gpi_instances", C.c_int64),
     ]
 
 
@@ -92,6 +93,7 @@ EXPORTS = [
     "tinympc_b200_solve",
     "tinympc_b200_solve_host",
     "tinympc_b200_get_stats",
+    "tinympc_b200_advance",
     "tinympc_b200_supported",
     "tinympc_b200_last_error",
     "tinympc_b200_version",

@@ -21,6 +21,27 @@ TM_DIMS(TM_DECL)
 
 namespace {
 
+// x0[b] <- (A x0[b] + B u[b][:,0]) + f ; one thread per (instance, row); matrices column-major in the blob
+template <typename T>
+__global__ void advance_kernel(int nx, int nu, int N, int64_t B, const T *__restrict__ blob, T *x0, const T *__restrict__ u) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = t < B * nx;
+    T r = T(0);
+    if (valid) {
+        const int64_t b = t / nx;
+        const int i = (int)(t - b * nx);
+        const T *A = blob, *Bm = blob + nx * nx, *f = Bm + nx * nu;
+        const T *xb = x0 + b * nx, *ub = u + b * (int64_t)(N - 1) * nu;
+        T ax = A[i] * xb[0];
+        for (int m = 1; m < nx; ++m) ax = ax + A[i + nx * m] * xb[m];
+        T bu = Bm[i] * ub[0];
+        for (int j = 1; j < nu; ++j) bu = bu + Bm[i + nx * j] * ub[j];
+        r = (ax + bu) + f[i];
+    }
+    __syncthreads();  // blockDim is a multiple of nx: all rows of an instance have read x0 before any row writes it
+    if (valid) x0[t] = r;
+}
+
 thread_local std::string g_err;
 int fail(int code, const std::string &msg) {
     g_err = msg;
@@ -116,7 +137,8 @@ struct tinympc_b200_solver {
     static constexpr int SLOTS = 3;
     DevBuf dio[SLOTS];
     PinBuf pin_in[SLOTS], pin_out[SLOTS];
-    cudaStream_t st_h2d = nullptr, st_k = nullptr, st_d2h = nullptr;
+    cudaStream_t st_h2d = nullptr, st_k = nullptr, st_d2h = nullptr, st_a = nullptr, st_b = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_ja = nullptr, ev_jb = nullptr;
     cudaEvent_t ev_in[SLOTS] = {}, ev_k[SLOTS] = {}, ev_out[SLOTS] = {};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
@@ -166,7 +188,19 @@ int resolve_family(const tinympc_b200_solver *s, const Features &ft, int *smem_o
     if (smem_out) *smem_out = smem;
     if (s->family == TINYMPC_KERNEL_GPI) return gpi_ok ? TINYMPC_KERNEL_GPI : -1;
     if (s->family == TINYMPC_KERNEL_TPI) return TINYMPC_KERNEL_TPI;
-    return gpi_ok ? TINYMPC_KERNEL_GPI : TINYMPC_KERNEL_TPI;
+    if (s->family == TINYMPC_KERNEL_HYBRID) return gpi_ok ? TINYMPC_KERNEL_HYBRID : -1;
+    return gpi_ok ? TINYMPC_KERNEL_GPI : TINYMPC_KERNEL_TPI;  // AUTO (HYBRID stays opt-in: profiles/README.md)
+}
+
+// Fraction of a batch the GPI kernel takes in HYBRID mode.  GPI (shared-memory bound: one CTA per SM, 4 warps,
+// no HBM traffic) and TPI (register/HBM bound, no shared memory) fit on an SM together; measured split in
+// profiles/ (override with TINYMPC_HYBRID_GPI_FRACTION for experiments).
+double hybrid_fraction(const tinympc_b200_solver *s) {
+    if (const char *e = std::getenv("TINYMPC_HYBRID_GPI_FRACTION")) {
+        double v = std::atof(e);
+        if (v >= 0.0 && v <= 1.0) return v;
+    }
+    return s->dtype == TINYMPC_F32 ? 0.55 : 0.5;
 }
 
 // carve the TPI structure-of-arrays workspace
@@ -276,37 +310,86 @@ int enqueue(tinympc_b200_solver *s, const tinympc_batch_t *io, cudaStream_t stre
     int smem = 0;
     const int family = resolve_family(s, ft, &smem);
     if (family < 0) return fail(TINYMPC_ERR_UNSUPPORTED, "GPI kernel requested but it does not support this problem (features or shared-memory footprint)");
+    int64_t launches = 0, ctas = 0;
     tmpc::LaunchDesc d;
     base_desc(s, d, ft);
-    d.family = family;
-    d.stream = stream;
-    const int64_t chunk = family == TINYMPC_KERNEL_TPI ? tpi_chunk_instances(s, ft, io->B) : io->B;
-    if (int rc = setup_workspace(s, d, ft, chunk, family)) return rc;
-    if (family == TINYMPC_KERNEL_GPI) {
-        if (s->queue.ensure(256)) return fail(TINYMPC_ERR_CUDA, "queue allocation failed");
-        CUDA_TRY(cudaMemsetAsync(s->queue.p, 0, 256, stream));
-        d.work_queue = s->queue.p;
-    }
     if (timed) CUDA_TRY(cudaEventRecord(s->ev0, stream));
-    int64_t launches = 0, ctas = 0;
-    for (int64_t b0 = 0; b0 < io->B; b0 += chunk) {
-        d.io = slice_batch(s, *io, b0, std::min<int64_t>(chunk, io->B - b0));
+    // instances [0, Bg) go to the GPI kernel, [Bg, B) to the TPI kernel
+    int64_t Bg = family == TINYMPC_KERNEL_GPI ? io->B : 0;
+    if (family == TINYMPC_KERNEL_HYBRID) {
+        const int64_t min_each = (int64_t)s->sm_count * 64;
+        Bg = (int64_t)(hybrid_fraction(s) * (double)io->B) / 32 * 32;
+        if (io->B < 2 * min_each || Bg < min_each) Bg = io->B;           // too small to split: GPI alone
+        else if (io->B - Bg < min_each) Bg = io->B;
+    }
+    const int64_t Bt = io->B - Bg;
+    const bool split = Bg > 0 && Bt > 0;
+    cudaStream_t sg = stream, stt = stream;
+    if (split) {
+        if (!s->st_a) {
+            CUDA_TRY(cudaStreamCreateWithFlags(&s->st_a, cudaStreamNonBlocking));
+            CUDA_TRY(cudaStreamCreateWithFlags(&s->st_b, cudaStreamNonBlocking));
+            CUDA_TRY(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&s->ev_ja, cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&s->ev_jb, cudaEventDisableTiming));
+        }
+        CUDA_TRY(cudaEventRecord(s->ev_fork, stream));
+        CUDA_TRY(cudaStreamWaitEvent(s->st_a, s->ev_fork, 0));
+        CUDA_TRY(cudaStreamWaitEvent(s->st_b, s->ev_fork, 0));
+        sg = s->st_a;
+        stt = s->st_b;
+    }
+    if (Bg > 0) {
+        d.family = TINYMPC_KERNEL_GPI;
+        d.stream = sg;
+        if (s->queue.ensure(256)) return fail(TINYMPC_ERR_CUDA, "queue allocation failed");
+        CUDA_TRY(cudaMemsetAsync(s->queue.p, 0, 256, sg));
+        d.work_queue = s->queue.p;
+        d.Bpad = (Bg + 31) / 32 * 32;
+        d.io = slice_batch(s, *io, 0, Bg);
         int rc = s->dim->launch(&d);
         if (rc == TINYMPC_ERR_CUDA) return fail(rc, std::string("kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
         if (rc) return fail(rc, "no compiled kernel for this (dtype, mode, family) combination");
         ++launches;
         ctas += d.out_ctas;
+        s->stats.lanes_per_instance = d.out_lanes_per_instance;
+        s->stats.instances_per_cta = d.out_instances_per_cta;
+        s->stats.smem_bytes_per_cta = d.out_smem;
+        s->stats.threads_per_cta = d.out_threads;
+    }
+    if (Bt > 0) {
+        d.family = TINYMPC_KERNEL_TPI;
+        d.stream = stt;
+        const int64_t chunk = tpi_chunk_instances(s, ft, Bt);
+        if (int rc = setup_workspace(s, d, ft, chunk, TINYMPC_KERNEL_TPI)) return rc;
+        for (int64_t b0 = 0; b0 < Bt; b0 += chunk) {
+            d.io = slice_batch(s, *io, Bg + b0, std::min<int64_t>(chunk, Bt - b0));
+            int rc = s->dim->launch(&d);
+            if (rc == TINYMPC_ERR_CUDA) return fail(rc, std::string("kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+            if (rc) return fail(rc, "no compiled kernel for this (dtype, mode, family) combination");
+            ++launches;
+            ctas += d.out_ctas;
+        }
+        if (Bg == 0) {
+            s->stats.lanes_per_instance = d.out_lanes_per_instance;
+            s->stats.instances_per_cta = d.out_instances_per_cta;
+            s->stats.smem_bytes_per_cta = d.out_smem;
+            s->stats.threads_per_cta = d.out_threads;
+        }
+    }
+    if (split) {
+        CUDA_TRY(cudaEventRecord(s->ev_ja, s->st_a));
+        CUDA_TRY(cudaEventRecord(s->ev_jb, s->st_b));
+        CUDA_TRY(cudaStreamWaitEvent(stream, s->ev_ja, 0));
+        CUDA_TRY(cudaStreamWaitEvent(stream, s->ev_jb, 0));
     }
     if (timed) CUDA_TRY(cudaEventRecord(s->ev1, stream));
     s->timed = timed;
     s->stats.instances = io->B;
     s->stats.kernel_launches = launches;
-    s->stats.kernel_family = family;
-    s->stats.lanes_per_instance = d.out_lanes_per_instance;
-    s->stats.instances_per_cta = d.out_instances_per_cta;
-    s->stats.smem_bytes_per_cta = d.out_smem;
+    s->stats.kernel_family = split ? TINYMPC_KERNEL_HYBRID : (Bg > 0 ? TINYMPC_KERNEL_GPI : TINYMPC_KERNEL_TPI);
     s->stats.ctas = (int)ctas;
-    s->stats.threads_per_cta = d.out_threads;
+    s->stats.gpi_instances = Bg;
     return TINYMPC_OK;
 }
 
@@ -457,6 +540,11 @@ int tinympc_b200_destroy(tinympc_b200_solver_t *s) {
     if (s->st_h2d) cudaStreamDestroy(s->st_h2d);
     if (s->st_k) cudaStreamDestroy(s->st_k);
     if (s->st_d2h) cudaStreamDestroy(s->st_d2h);
+    if (s->st_a) cudaStreamDestroy(s->st_a);
+    if (s->st_b) cudaStreamDestroy(s->st_b);
+    if (s->ev_fork) cudaEventDestroy(s->ev_fork);
+    if (s->ev_ja) cudaEventDestroy(s->ev_ja);
+    if (s->ev_jb) cudaEventDestroy(s->ev_jb);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     delete s;
@@ -479,7 +567,7 @@ int tinympc_b200_get_settings(const tinympc_b200_solver_t *s, tinympc_settings_t
 int tinympc_b200_set_mode(tinympc_b200_solver_t *s, int32_t mode, int32_t family) {
     if (!s) return fail(TINYMPC_ERR_ARG, "null solver");
     if (mode != TINYMPC_MODE_STRICT && mode != TINYMPC_MODE_FAST) return fail(TINYMPC_ERR_ARG, "bad mode");
-    if (family < TINYMPC_KERNEL_AUTO || family > TINYMPC_KERNEL_GPI) return fail(TINYMPC_ERR_ARG, "bad kernel family");
+    if (family < TINYMPC_KERNEL_AUTO || family > TINYMPC_KERNEL_HYBRID) return fail(TINYMPC_ERR_ARG, "bad kernel family");
     s->mode = mode;
     s->family = family;
     return TINYMPC_OK;
@@ -489,6 +577,23 @@ int tinympc_b200_solve(tinympc_b200_solver_t *s, const tinympc_batch_t *io, void
     if (!s || !io) return fail(TINYMPC_ERR_ARG, "null argument");
     CUDA_TRY(cudaSetDevice(s->device));
     return enqueue(s, io, (cudaStream_t)cuda_stream, true);
+}
+
+int tinympc_b200_advance(tinympc_b200_solver_t *s, int64_t B, void *x0, const void *u, void *cuda_stream) {
+    if (!s || !x0 || !u) return fail(TINYMPC_ERR_ARG, "null argument");
+    if (B <= 0) return TINYMPC_OK;
+    CUDA_TRY(cudaSetDevice(s->device));
+    // threads per block = a multiple of nx so that all rows of an instance read x0 before any row writes it
+    const int per = std::max(1, 256 / s->nx) * s->nx;
+    const int64_t total = B * s->nx;
+    const unsigned blocks = (unsigned)((total + per - 1) / per);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (s->dtype == TINYMPC_F32)
+        advance_kernel<float><<<blocks, per, 0, st>>>(s->nx, s->nu, s->N, B, (const float *)s->d_blob.p, (float *)x0, (const float *)u);
+    else
+        advance_kernel<double><<<blocks, per, 0, st>>>(s->nx, s->nu, s->N, B, (const double *)s->d_blob.p, (double *)x0, (const double *)u);
+    CUDA_TRY(cudaGetLastError());
+    return TINYMPC_OK;
 }
 
 int tinympc_b200_get_stats(const tinympc_b200_solver_t *s, tinympc_b200_stats_t *out) {

@@ -23,32 +23,30 @@
 
 namespace tmpc {
 
-template <int NX, int NU, int L>
+template <int NX, int NU, int L, int ES>
 struct GpiCfg {
     static constexpr int RX = (NX + L - 1) / L;
     static constexpr int RU = (NU + L - 1) / L;
-    static constexpr int IPW = 32 / L;  // instances per warp
+    static constexpr int IPW = 32 / L;      // instances per warp
+    static constexpr int W = 16 / ES;       // elements per 16-byte shared-memory vector
+    static constexpr int PV = RX + RU;      // values a lane owns per knot point (state rows, then input rows)
+    static constexpr int PVP = (PV + W - 1) / W * W;
+    static constexpr int NPV = PVP / W;     // vectors per pack
+    static constexpr int NXP = (L * RX + W - 1) / W * W;  // gather buffer width (state vectors)
+    static constexpr int NUP = (L * RU + W - 1) / W * W;  // gather buffer width (input vectors)
+    static constexpr int GBUF = IPW * (NXP > NUP ? NXP : NUP);
     // registers needed for the per-lane matrix rows (in elements of T)
     static constexpr int MAT_REGS = RX * (2 * NX + 2 * NU + 3) + RU * (2 * NX + NU + 2);
-    // shared-memory words (elements of T) per warp for horizon N
-    __host__ __device__ static constexpr size_t warp_elems(int N) { return (size_t)32 * ((size_t)N * RX * 2 + (size_t)(N - 1) * RU * 3); }
+    // shared-memory elements per warp for horizon N: primal pack + dual pack per (k, lane), d, gather scratch
+    __host__ __device__ static constexpr size_t warp_elems(int N) {
+        return (size_t)N * 32 * PVP * 2 + (size_t)(N - 1) * RU * 32 + GBUF;
+    }
 };
 
 template <typename T, int NX, int NU, int L>
 constexpr bool gpi_feasible() {
     // keep the matrix rows + working set under the 255-register ceiling
-    return GpiCfg<NX, NU, L>::MAT_REGS * (int)(sizeof(T) / 4) <= 150;
-}
-
-// all-gather of R values per lane inside an L-lane group -> full[j*R + a] = value a of lane j (absolute
-// lane order, so that dot products run over ascending column index as the oracle does)
-template <typename T, int R, int L, int NE>
-__device__ __forceinline__ void gather(const T (&own)[R], T (&full)[NE]) {
-#pragma unroll
-    for (int j = 0; j < L; ++j)
-#pragma unroll
-        for (int a = 0; a < R; ++a)
-            if (j * R + a < NE) full[j * R + a] = __shfl_sync(0xffffffffu, own[a], j, L);
+    return GpiCfg<NX, NU, L, (int)sizeof(T)>::MAT_REGS * (int)(sizeof(T) / 4) <= 150;
 }
 
 template <typename T, int L>
@@ -63,8 +61,8 @@ __device__ __forceinline__ T group_max(T v) {
 
 constexpr int GPI_MAX_WARPS = 8;
 
-// Shared-memory accessors on 32-bit shared-window addresses: keeps the generic->shared conversion
-// (S2UR SR_CgaCtaId + ULEA) and 64-bit address arithmetic out of the hot loops.
+// Shared-memory accessors on 32-bit shared-window addresses (no generic->shared conversion, no 64-bit
+// address arithmetic in the hot loops).  16-byte vector forms move a whole per-lane pack per instruction.
 __device__ __forceinline__ float lds(unsigned a, float) {
     float v;
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
@@ -77,6 +75,18 @@ __device__ __forceinline__ double lds(unsigned a, double) {
 }
 __device__ __forceinline__ void sts(unsigned a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
 __device__ __forceinline__ void sts(unsigned a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+__device__ __forceinline__ void ldsv(unsigned a, float (&v)[4]) {
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldsv(unsigned a, double (&v)[2]) {
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "r"(a));
+}
+__device__ __forceinline__ void stsv(unsigned a, const float (&v)[4]) {
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+}
+__device__ __forceinline__ void stsv(unsigned a, const double (&v)[2]) {
+    asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(a), "d"(v[0]), "d"(v[1]) : "memory");
+}
 
 template <bool B>
 struct BoolTag {
@@ -100,9 +110,11 @@ __device__ __forceinline__ double absmax(double m, double d) { return fmax(m, fa
 template <typename T, int NX, int NU, int L, bool FAST>
 __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
     gpi_solve_kernel(const __grid_constant__ KParams<T, NX, NU> P, const T *__restrict__ gmat, unsigned long long *queue) {
-    using Cfg = GpiCfg<NX, NU, L>;
-    constexpr int RX = Cfg::RX, RU = Cfg::RU, IPW = Cfg::IPW;
+    using Cfg = GpiCfg<NX, NU, L, (int)sizeof(T)>;
+    constexpr int RX = Cfg::RX, RU = Cfg::RU, IPW = Cfg::IPW, W = Cfg::W, PVP = Cfg::PVP, NPV = Cfg::NPV;
+    constexpr int NXP = Cfg::NXP, NUP = Cfg::NUP;
     constexpr bool EXACT = (RX * L == NX) && (RU * L == NU);  // no padding rows: predicates vanish
+    constexpr unsigned ES = (unsigned)sizeof(T);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = P.N;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -146,7 +158,7 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
     // per-lane matrix rows (registers)
     T mAmBKt[RX][NX], mKt[RX][NU], mA[RX][NX], mB[RX][NU], vQd[RX], vAPf[RX], vf[RX];
     T mBt[RU][NX], mQuu[RU][NU], mK[RU][NX], vRd[RU], vBPf[RU];
-    bool xv[RX], uv[RU];  // row validity (padding rows compute zeros and never store)
+    bool xv[RX], uv[RU];  // row validity (padding rows compute zeros)
 #pragma unroll
     for (int a = 0; a < RX; ++a) {
         const int i = l * RX + a;
@@ -183,29 +195,68 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
     }
     __syncthreads();  // staging area is reused as state below
 
-    // ---- shared-memory state of this warp: [k][slot a][lane]; element offsets fit in 32 bits ----
+    // ---- shared-memory state of this warp ----
+    //   PA[k][lane][PVP] : primal pack  (vnew rows of this lane, then znew rows)      16-byte vectors,
+    //   PB[k][lane][PVP] : dual pack    (g rows, then y rows)                          conflict free
+    //   D [k][b][lane]   : d
+    //   GB[...]          : gather scratch (one vector of one instance per row)
     const int warp_elems = (int)Cfg::warp_elems(N);
     T *wbase = reinterpret_cast<T *>(smem_raw) + (size_t)warp * warp_elems;
-    T *sV = wbase + lane;                 // vnew : N * RX * 32
-    T *sG = sV + N * RX * 32;             // g
-    T *sZ = sG + N * RX * 32;             // znew : (N-1) * RU * 32
-    T *sY = sZ + (N - 1) * RU * 32;       // y
-    T *sD = sY + (N - 1) * RU * 32;       // d
-    constexpr int SX = RX * 32, SU = RU * 32;  // per-k strides
-    constexpr unsigned ES = (unsigned)sizeof(T);
-    const unsigned aV = (unsigned)__cvta_generic_to_shared(sV), aG = (unsigned)__cvta_generic_to_shared(sG),
-                   aZ = (unsigned)__cvta_generic_to_shared(sZ), aY = (unsigned)__cvta_generic_to_shared(sY),
-                   aD = (unsigned)__cvta_generic_to_shared(sD);
-    auto LV = [&](int k, int a) { return lds(aV + (unsigned)(k * SX + a * 32) * ES, T()); };
-    auto LG = [&](int k, int a) { return lds(aG + (unsigned)(k * SX + a * 32) * ES, T()); };
-    auto LZ = [&](int k, int b) { return lds(aZ + (unsigned)(k * SU + b * 32) * ES, T()); };
-    auto LY = [&](int k, int b) { return lds(aY + (unsigned)(k * SU + b * 32) * ES, T()); };
-    auto LD = [&](int k, int b) { return lds(aD + (unsigned)(k * SU + b * 32) * ES, T()); };
-    auto SV_ = [&](int k, int a, T v) { sts(aV + (unsigned)(k * SX + a * 32) * ES, v); };
-    auto SG_ = [&](int k, int a, T v) { sts(aG + (unsigned)(k * SX + a * 32) * ES, v); };
-    auto SZ_ = [&](int k, int b, T v) { sts(aZ + (unsigned)(k * SU + b * 32) * ES, v); };
-    auto SY_ = [&](int k, int b, T v) { sts(aY + (unsigned)(k * SU + b * 32) * ES, v); };
-    auto SD_ = [&](int k, int b, T v) { sts(aD + (unsigned)(k * SU + b * 32) * ES, v); };
+    T *gPA = wbase, *gPB = gPA + N * 32 * PVP, *gD = gPB + N * 32 * PVP, *gGB = gD + (N - 1) * RU * 32;
+    const unsigned aPA = (unsigned)__cvta_generic_to_shared(gPA) + (unsigned)(lane * PVP) * ES;
+    const unsigned aPB = (unsigned)__cvta_generic_to_shared(gPB) + (unsigned)(lane * PVP) * ES;
+    const unsigned aD = (unsigned)__cvta_generic_to_shared(gD) + (unsigned)lane * ES;
+    const unsigned aGB = (unsigned)__cvta_generic_to_shared(gGB);
+    constexpr unsigned KSTR = 32u * PVP * ES;  // bytes per knot point in PA / PB
+    constexpr unsigned DSTR = (unsigned)RU * 32u * ES;
+    auto load_pack = [&](unsigned base, int k, T (&v)[PVP]) {
+#pragma unroll
+        for (int c = 0; c < NPV; ++c) {
+            T t[W];
+            ldsv(base + (unsigned)k * KSTR + (unsigned)(c * W) * ES, t);
+#pragma unroll
+            for (int e = 0; e < W; ++e) v[c * W + e] = t[e];
+        }
+    };
+    auto store_pack = [&](unsigned base, int k, const T (&v)[PVP]) {
+#pragma unroll
+        for (int c = 0; c < NPV; ++c) {
+            T t[W];
+#pragma unroll
+            for (int e = 0; e < W; ++e) t[e] = v[c * W + e];
+            stsv(base + (unsigned)k * KSTR + (unsigned)(c * W) * ES, t);
+        }
+    };
+    // all-gather inside the lane group through shared memory: every lane stores its R values, then reads the
+    // whole vector with 16-byte broadcast loads (absolute row order -> ascending-k dot products as in the oracle)
+    auto gather_x = [&](const T (&own)[RX], T (&full)[NX]) {
+        __syncwarp();
+#pragma unroll
+        for (int a = 0; a < RX; ++a) sts(aGB + (unsigned)(slot * NXP + l * RX + a) * ES, own[a]);
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < NXP / W; ++c) {
+            T t[W];
+            ldsv(aGB + (unsigned)(slot * NXP + c * W) * ES, t);
+#pragma unroll
+            for (int e = 0; e < W; ++e)
+                if (c * W + e < NX) full[c * W + e] = t[e];
+        }
+    };
+    auto gather_u = [&](const T (&own)[RU], T (&full)[NU]) {
+        __syncwarp();
+#pragma unroll
+        for (int b = 0; b < RU; ++b) sts(aGB + (unsigned)(slot * NUP + l * RU + b) * ES, own[b]);
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < NUP / W; ++c) {
+            T t[W];
+            ldsv(aGB + (unsigned)(slot * NUP + c * W) * ES, t);
+#pragma unroll
+            for (int e = 0; e < W; ++e)
+                if (c * W + e < NU) full[c * W + e] = t[e];
+        }
+    };
 
     const bool cold = P.cold != 0;
     const int64_t ngroups = (P.B + IPW - 1) / IPW;
@@ -223,6 +274,9 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
         hiU[b] = (enu && uv[b]) ? __ldg(P.u_max + l * RU + b) : T(0);
     }
     const bool keep_v = (P.s_v != nullptr) || (P.s_z != nullptr);
+    // where element (k, row i) of instance-slot s lives inside a pack region
+    auto idx_x = [&](int s, int k, int i) { return (k * 32 + s * L + i / RX) * PVP + (i % RX); };
+    auto idx_u = [&](int s, int k, int j) { return (k * 32 + s * L + j / RU) * PVP + RX + (j % RU); };
 
     for (;;) {
         // ---- next group of IPW instances ----
@@ -237,32 +291,33 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
         const T *xrefp = P.Xref + (P.xref_pi ? offx : 0) + l * RX;
         const T *urefp = P.Uref ? P.Uref + (P.uref_pi ? offu : 0) + l * RU : nullptr;
 
-        // ---- prologue: zero (cold) or load (warm) the shared-memory state ----
-        if (cold) {
+        // ---- prologue: zero the state (also defines padding slots), then load a warm start ----
+        {
             float4 *w4 = reinterpret_cast<float4 *>(wbase);
             const int n4 = (int)((size_t)warp_elems * sizeof(T) / 16);
             for (int w = lane; w < n4; w += 32) w4[w] = make_float4(0.f, 0.f, 0.f, 0.f);
-        } else {
-            T *uV = wbase, *uG = uV + N * SX, *uZ = uG + N * SX, *uY = uZ + (N - 1) * SU;
+        }
+        __syncwarp();
+        if (!cold) {
             for (int s = 0; s < IPW; ++s) {
                 const int64_t ib = (int64_t)grp * IPW + s;
                 if (ib >= P.B) break;
                 const int64_t ox = ib * (int64_t)N * NX, ou = ib * (int64_t)(N - 1) * NU;
                 for (int e = lane; e < N * NX; e += 32) {
                     const int k = e / NX, i = e - k * NX;
-                    const int w = (k * RX + (i % RX)) * 32 + s * L + i / RX;
-                    uV[w] = P.s_vnew ? P.s_vnew[ox + e] : T(0);
-                    uG[w] = P.s_g ? P.s_g[ox + e] : T(0);
+                    const int w = idx_x(s, k, i);
+                    gPA[w] = P.s_vnew ? P.s_vnew[ox + e] : T(0);
+                    gPB[w] = P.s_g ? P.s_g[ox + e] : T(0);
                 }
                 for (int e = lane; e < (N - 1) * NU; e += 32) {
                     const int k = e / NU, j = e - k * NU;
-                    const int w = (k * RU + (j % RU)) * 32 + s * L + j / RU;
-                    uZ[w] = P.s_znew ? P.s_znew[ou + e] : T(0);
-                    uY[w] = P.s_y ? P.s_y[ou + e] : T(0);
+                    const int w = idx_u(s, k, j);
+                    gPA[w] = P.s_znew ? P.s_znew[ou + e] : T(0);
+                    gPB[w] = P.s_y ? P.s_y[ou + e] : T(0);
                 }
             }
+            __syncwarp();
         }
-        __syncwarp();
         // x0 (own rows) and the iteration-invariant part of the terminal cost: -(Pinf^T xref_{N-1})
         T x0o[RX], pterm[RX];
         {
@@ -285,21 +340,21 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
         bool active = live;
         T res_px = T(0), res_dx = T(0), res_pu = T(0), res_du = T(0);
 
-        // linear cost of column k for this lane's rows: q = -(xref*Qd) - rho*(vnew - g), r = -(uref*Rd) - rho*(znew - y)
-        auto cost_x = [&](int k, const T *xp, T (&q)[RX]) {  // xp -> this lane's rows of Xref column k
+        // linear cost of column k for this lane's rows (update_linear_cost, admm.cpp:266-280):
+        //   q = -(xref*Qd) - rho*(vnew - g),  r = -(uref*Rd) - rho*(znew - y)
+        auto cost = [&](int k, const T *xp, const T *up, T (&q)[RX], T (&r)[RU]) {
+            T pa[PVP], pb[PVP];
+            load_pack(aPA, k, pa);
+            load_pack(aPB, k, pb);
 #pragma unroll
             for (int a = 0; a < RX; ++a) {
                 const T xr = xv[a] ? __ldg(xp + a) : T(0);
-                const T vn = xv[a] ? LV(k, a) : T(0), g = xv[a] ? LG(k, a) : T(0);
-                q[a] = nmac<FAST>(-(xr * vQd[a]), rho, vn - g);
+                q[a] = nmac<FAST>(-(xr * vQd[a]), rho, pa[a] - pb[a]);
             }
-        };
-        auto cost_u = [&](int k, const T *up, T (&r)[RU]) {
 #pragma unroll
             for (int b = 0; b < RU; ++b) {
                 const T ur = (up && uv[b]) ? __ldg(up + b) : T(0);
-                const T zn = uv[b] ? LZ(k, b) : T(0), y = uv[b] ? LY(k, b) : T(0);
-                r[b] = nmac<FAST>(-(ur * vRd[b]), rho, zn - y);
+                r[b] = nmac<FAST>(-(ur * vRd[b]), rho, pa[RX + b] - pb[RX + b]);
             }
         };
 
@@ -310,34 +365,20 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
             T xo[RX], Xf[NX];
 #pragma unroll
             for (int a = 0; a < RX; ++a) xo[a] = x0o[a];
-            gather<T, RX, L, NX>(xo, Xf);
-            T gc[RX], vc[RX], yc[RU], zc[RU], dc[RU];  // state of the current column (prefetched)
+            gather_x(xo, Xf);
+            T pa[PVP], pb[PVP], dc[RU];  // state of the current column (prefetched)
+            load_pack(aPA, 0, pa);
+            load_pack(aPB, 0, pb);
 #pragma unroll
-            for (int a = 0; a < RX; ++a) {
-                gc[a] = xv[a] ? LG(0, a) : T(0);
-                vc[a] = xv[a] ? LV(0, a) : T(0);
-            }
-#pragma unroll
-            for (int b = 0; b < RU; ++b) {
-                yc[b] = uv[b] ? LY(0, b) : T(0);
-                zc[b] = uv[b] ? LZ(0, b) : T(0);
-                dc[b] = uv[b] ? LD(0, b) : T(0);
-            }
+            for (int b = 0; b < RU; ++b) dc[b] = lds(aD + (unsigned)(b * 32) * ES, T());
             for (int k = 0; k < N; ++k) {
-                // prefetch the next column's state while this one is being processed
-                T gn_[RX], vn_[RX], yn_[RU], zn_[RU], dn_[RU];
-                const int kx = (k + 1 < N) ? k + 1 : k, ku = (k + 2 < N) ? k + 1 : ((N >= 2) ? N - 2 : 0);  // clamped: always valid
+                // prefetch the next column's state while this one is being processed (indices clamped: always valid)
+                T pan[PVP], pbn[PVP], dn_[RU];
+                const int kx = (k + 1 < N) ? k + 1 : k, ku = (k + 2 < N) ? k + 1 : ((N >= 2) ? N - 2 : 0);
+                load_pack(aPA, kx, pan);
+                load_pack(aPB, kx, pbn);
 #pragma unroll
-                for (int a = 0; a < RX; ++a) {
-                    gn_[a] = xv[a] ? LG(kx, a) : T(0);
-                    vn_[a] = xv[a] ? LV(kx, a) : T(0);
-                }
-#pragma unroll
-                for (int b = 0; b < RU; ++b) {
-                    yn_[b] = uv[b] ? LY(ku, b) : T(0);
-                    zn_[b] = uv[b] ? LZ(ku, b) : T(0);
-                    dn_[b] = uv[b] ? LD(ku, b) : T(0);
-                }
+                for (int b = 0; b < RU; ++b) dn_[b] = lds(aD + (unsigned)ku * DSTR + (unsigned)(b * 32) * ES, T());
                 if (tvb) {
 #pragma unroll
                     for (int a = 0; a < RX; ++a) {
@@ -361,24 +402,27 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
                         for (int m = 1; m < NX; ++m) t = mac<FAST>(t, mK[b][m], Xf[m]);
                         u[b] = (-t) - dc[b];
                     }
-                    gather<T, RU, L, NU>(u, Uf);
+                    gather_u(u, Uf);
+                }
+                T na[PVP], nb[PVP];  // new packs of this column
+#pragma unroll
+                for (int e = 0; e < PVP; ++e) {
+                    na[e] = pa[e];
+                    nb[e] = pb[e];
                 }
                 // state column k: vnew = clamp(x + g), g += x - vnew
 #pragma unroll
                 for (int a = 0; a < RX; ++a) {
-                    T vo = vc[a];
+                    T vo = pa[a];
                     if constexpr (SLOW) {
                         if (vin) vo = (P.s_v && xv[a]) ? P.s_v[offx + (int64_t)k * NX + l * RX + a] : T(0);
                     }
-                    T v = xo[a] + gc[a];
+                    T v = xo[a] + pb[a];
                     if (enx) v = clamp_box<FAST>(v, loX[a], hiX[a]);
-                    const T gnew = (gc[a] + xo[a]) - v;
-                    if (active && xv[a]) {
-                        SV_(k, a, v);
-                        SG_(k, a, gnew);
-                        if constexpr (SLOW) {
-                            if (P.s_v) P.s_v[offx + (int64_t)k * NX + l * RX + a] = vo;  // work->v of this iteration
-                        }
+                    na[a] = v;
+                    nb[a] = (pb[a] + xo[a]) - v;
+                    if constexpr (SLOW) {
+                        if (active && xv[a] && P.s_v) P.s_v[offx + (int64_t)k * NX + l * RX + a] = vo;  // work->v of this iteration
                     }
                     rpx = absmax(rpx, xo[a] - v);
                     rdx = absmax(rdx, vo - v);
@@ -386,23 +430,26 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
                 if (k < N - 1) {
 #pragma unroll
                     for (int b = 0; b < RU; ++b) {
-                        T zo = zc[b];
+                        T zo = pa[RX + b];
                         if constexpr (SLOW) {
                             if (vin) zo = (P.s_z && uv[b]) ? P.s_z[offu + (int64_t)k * NU + l * RU + b] : T(0);
                         }
-                        T z = u[b] + yc[b];
+                        T z = u[b] + pb[RX + b];
                         if (enu) z = clamp_box<FAST>(z, loU[b], hiU[b]);
-                        const T ynew = (yc[b] + u[b]) - z;
-                        if (active && uv[b]) {
-                            SZ_(k, b, z);
-                            SY_(k, b, ynew);
-                            if constexpr (SLOW) {
-                                if (P.s_z) P.s_z[offu + (int64_t)k * NU + l * RU + b] = zo;
-                            }
+                        na[RX + b] = z;
+                        nb[RX + b] = (pb[RX + b] + u[b]) - z;
+                        if constexpr (SLOW) {
+                            if (active && uv[b] && P.s_z) P.s_z[offu + (int64_t)k * NU + l * RU + b] = zo;
                         }
                         rpu = absmax(rpu, u[b] - z);
                         rdu = absmax(rdu, zo - z);
                     }
+                }
+                if (active) {
+                    store_pack(aPA, k, na);
+                    store_pack(aPB, k, nb);
+                }
+                if (k < N - 1) {
                     // x_{k+1} = (A x_k + B u_k) + f
 #pragma unroll
                     for (int a = 0; a < RX; ++a) {
@@ -414,19 +461,15 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
                         for (int j = 1; j < NU; ++j) bu = mac<FAST>(bu, mB[a][j], Uf[j]);
                         xo[a] = (ax + bu) + vf[a];
                     }
-                    gather<T, RX, L, NX>(xo, Xf);
+                    gather_x(xo, Xf);
                 }
 #pragma unroll
-                for (int a = 0; a < RX; ++a) {
-                    gc[a] = gn_[a];
-                    vc[a] = vn_[a];
+                for (int e = 0; e < PVP; ++e) {
+                    pa[e] = pan[e];
+                    pb[e] = pbn[e];
                 }
 #pragma unroll
-                for (int b = 0; b < RU; ++b) {
-                    yc[b] = yn_[b];
-                    zc[b] = zn_[b];
-                    dc[b] = dn_[b];
-                }
+                for (int b = 0; b < RU; ++b) dc[b] = dn_[b];
             }
         };
 
@@ -435,27 +478,27 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
 
             // ---- terminal cost + backward pass (update_linear_cost fused, software-pipelined by one column) ----
             T po[RX], Pf[NX];
+            {
+                T pa[PVP], pb[PVP];
+                load_pack(aPA, N - 1, pa);
+                load_pack(aPB, N - 1, pb);
 #pragma unroll
-            for (int a = 0; a < RX; ++a) {
-                const T vn = xv[a] ? LV(N - 1, a) : T(0), g = xv[a] ? LG(N - 1, a) : T(0);
-                po[a] = nmac<FAST>(pterm[a], rho, vn - g);
+                for (int a = 0; a < RX; ++a) po[a] = nmac<FAST>(pterm[a], rho, pa[a] - pb[a]);
             }
-            gather<T, RX, L, NX>(po, Pf);
+            gather_x(po, Pf);
             T q[RX], r[RU], Rf[NU];
             const T *xp = xrefp + (int64_t)(N - 2) * NX;
             const T *up = urefp ? urefp + (int64_t)(N - 2) * NU : nullptr;
-            cost_x(N - 2, xp, q);
-            cost_u(N - 2, up, r);
-            gather<T, RU, L, NU>(r, Rf);
+            cost(N - 2, xp, up, q, r);
+            gather_u(r, Rf);
             for (int k = N - 2; k >= 0; --k) {
                 // next column's cost (independent of p): overlaps with the dot-product chains below
                 T qn[RX], rn[RU], Rn[NU];
                 if (k > 0) {
                     xp -= NX;
                     if (up) up -= NU;
-                    cost_x(k - 1, xp, qn);
-                    cost_u(k - 1, up, rn);
-                    gather<T, RU, L, NU>(rn, Rn);
+                    cost(k - 1, xp, up, qn, rn);
+                    gather_u(rn, Rn);
                 }
                 // d_k = Quu_inv ((B^T p_{k+1} + r_k) + BPf)
                 T s[RU], Sf[NU];
@@ -466,7 +509,7 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
                     for (int m = 1; m < NX; ++m) t = mac<FAST>(t, mBt[b][m], Pf[m]);
                     s[b] = (t + r[b]) + vBPf[b];
                 }
-                gather<T, RU, L, NU>(s, Sf);
+                gather_u(s, Sf);
                 // p_k = ((q_k + AmBKt p_{k+1}) - Kinf^T r_k) + APf
 #pragma unroll
                 for (int a = 0; a < RX; ++a) {
@@ -478,13 +521,13 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
                     for (int j = 1; j < NU; ++j) kr = mac<FAST>(kr, mKt[a][j], Rf[j]);
                     po[a] = ((q[a] + acc) - kr) + vAPf[a];
                 }
-                gather<T, RX, L, NX>(po, Pf);
+                gather_x(po, Pf);
 #pragma unroll
                 for (int b = 0; b < RU; ++b) {
                     T t = mQuu[b][0] * Sf[0];
 #pragma unroll
                     for (int m = 1; m < NU; ++m) t = mac<FAST>(t, mQuu[b][m], Sf[m]);
-                    if (active && uv[b]) SD_(k, b, t);
+                    if (active && uv[b]) sts(aD + (unsigned)k * DSTR + (unsigned)(b * 32) * ES, t);
                 }
 #pragma unroll
                 for (int a = 0; a < RX; ++a) q[a] = qn[a];
@@ -531,62 +574,61 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
         }
         __syncwarp();
         // solution->x = vnew, solution->u = znew; work->vnew/znew/g/y; coalesced transposing copy per instance
-        {
-            const T *uV = wbase, *uG = uV + N * SX, *uZ = uG + N * SX, *uY = uZ + (N - 1) * SU;
-            for (int s = 0; s < IPW; ++s) {
-                const int64_t ib = (int64_t)grp * IPW + s;
-                if (ib >= P.B) break;
-                const int64_t ox = ib * (int64_t)N * NX, ou = ib * (int64_t)(N - 1) * NU;
-                const int s_solved = __shfl_sync(0xffffffffu, solved, s * L);
-                const int s_it = __shfl_sync(0xffffffffu, it_done, s * L);
-                for (int e = lane; e < N * NX; e += 32) {
-                    const int k = e / NX, i = e - k * NX;
-                    const int w = (k * RX + (i % RX)) * 32 + s * L + i / RX;
-                    const T v = uV[w];
-                    P.sol_x[ox + e] = v;
-                    if (P.s_vnew) P.s_vnew[ox + e] = v;
-                    if (P.s_g) P.s_g[ox + e] = uG[w];
-                    // work->v: previous vnew if the solve converged (streamed out during the last forward pass),
-                    // else = vnew (admm.cpp:445); untouched when no iteration ran on a warm start
-                    if (P.s_v && !s_solved && s_it > 0) P.s_v[ox + e] = v;
-                    else if (P.s_v && cold && s_it == 0) P.s_v[ox + e] = T(0);
-                }
-                for (int e = lane; e < (N - 1) * NU; e += 32) {
-                    const int k = e / NU, j = e - k * NU;
-                    const int w = (k * RU + (j % RU)) * 32 + s * L + j / RU;
-                    const T z = uZ[w];
-                    P.sol_u[ou + e] = z;
-                    if (P.s_znew) P.s_znew[ou + e] = z;
-                    if (P.s_y) P.s_y[ou + e] = uY[w];
-                    if (P.s_z && !s_solved && s_it > 0) P.s_z[ou + e] = z;
-                    else if (P.s_z && cold && s_it == 0) P.s_z[ou + e] = T(0);
-                }
+        for (int s = 0; s < IPW; ++s) {
+            const int64_t ib = (int64_t)grp * IPW + s;
+            if (ib >= P.B) break;
+            const int64_t ox = ib * (int64_t)N * NX, ou = ib * (int64_t)(N - 1) * NU;
+            const int s_solved = __shfl_sync(0xffffffffu, solved, s * L);
+            const int s_it = __shfl_sync(0xffffffffu, it_done, s * L);
+            for (int e = lane; e < N * NX; e += 32) {
+                const int k = e / NX, i = e - k * NX;
+                const int w = idx_x(s, k, i);
+                const T v = gPA[w];
+                P.sol_x[ox + e] = v;
+                if (P.s_vnew) P.s_vnew[ox + e] = v;
+                if (P.s_g) P.s_g[ox + e] = gPB[w];
+                // work->v: previous vnew if the solve converged (streamed out during the last forward pass),
+                // else = vnew (admm.cpp:445); untouched when no iteration ran on a warm start
+                if (P.s_v && !s_solved && s_it > 0) P.s_v[ox + e] = v;
+                else if (P.s_v && cold && s_it == 0) P.s_v[ox + e] = T(0);
+            }
+            for (int e = lane; e < (N - 1) * NU; e += 32) {
+                const int k = e / NU, j = e - k * NU;
+                const int w = idx_u(s, k, j);
+                const T z = gPA[w];
+                P.sol_u[ou + e] = z;
+                if (P.s_znew) P.s_znew[ou + e] = z;
+                if (P.s_y) P.s_y[ou + e] = gPB[w];
+                if (P.s_z && !s_solved && s_it > 0) P.s_z[ou + e] = z;
+                else if (P.s_z && cold && s_it == 0) P.s_z[ou + e] = T(0);
             }
         }
         // work->x / work->u: replay the last rollout from d and x0 (bit-identical to the last forward pass),
-        // staging it in the (now dead) vnew / znew regions so that the write-back is coalesced too
+        // staging it in the (now dead) primal pack so that the write-back is coalesced too
         if (P.s_x || P.s_u) {
             __syncwarp();
             T xo[RX], Xf[NX];
 #pragma unroll
             for (int a = 0; a < RX; ++a) xo[a] = x0o[a];
-            gather<T, RX, L, NX>(xo, Xf);
+            gather_x(xo, Xf);
             for (int k = 0; k < N; ++k) {
+                T na[PVP];
 #pragma unroll
-                for (int a = 0; a < RX; ++a)
-                    if (xv[a]) SV_(k, a, xo[a]);
+                for (int e = 0; e < PVP; ++e) na[e] = T(0);
+#pragma unroll
+                for (int a = 0; a < RX; ++a) na[a] = xo[a];
                 if (k < N - 1) {
                     T u[RU], Uf[NU];
 #pragma unroll
                     for (int b = 0; b < RU; ++b) {
-                        const T d = uv[b] ? LD(k, b) : T(0);
+                        const T d = lds(aD + (unsigned)k * DSTR + (unsigned)(b * 32) * ES, T());
                         T t = mK[b][0] * Xf[0];
 #pragma unroll
                         for (int m = 1; m < NX; ++m) t = mac<FAST>(t, mK[b][m], Xf[m]);
                         u[b] = (-t) - d;
-                        if (uv[b]) SZ_(k, b, u[b]);
+                        na[RX + b] = u[b];
                     }
-                    gather<T, RU, L, NU>(u, Uf);
+                    gather_u(u, Uf);
 #pragma unroll
                     for (int a = 0; a < RX; ++a) {
                         T ax = mA[a][0] * Xf[0];
@@ -597,11 +639,11 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
                         for (int j = 1; j < NU; ++j) bu = mac<FAST>(bu, mB[a][j], Uf[j]);
                         xo[a] = (ax + bu) + vf[a];
                     }
-                    gather<T, RX, L, NX>(xo, Xf);
                 }
+                store_pack(aPA, k, na);
+                if (k < N - 1) gather_x(xo, Xf);
             }
             __syncwarp();
-            const T *uV = wbase, *uZ = uV + 2 * N * SX;
             for (int s = 0; s < IPW; ++s) {
                 const int64_t ib = (int64_t)grp * IPW + s;
                 if (ib >= P.B) break;
@@ -610,15 +652,13 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
                 if (P.s_x)
                     for (int e = lane; e < N * NX; e += 32) {
                         const int k = e / NX, i = e - k * NX;
-                        const int w = (k * RX + (i % RX)) * 32 + s * L + i / RX;
-                        if (s_it > 0 || k == 0) P.s_x[ox + e] = uV[w];
+                        if (s_it > 0 || k == 0) P.s_x[ox + e] = gPA[idx_x(s, k, i)];
                         else if (cold) P.s_x[ox + e] = T(0);
                     }
                 if (P.s_u)
                     for (int e = lane; e < (N - 1) * NU; e += 32) {
                         const int k = e / NU, j = e - k * NU;
-                        const int w = (k * RU + (j % RU)) * 32 + s * L + j / RU;
-                        if (s_it > 0) P.s_u[ou + e] = uZ[w];
+                        if (s_it > 0) P.s_u[ou + e] = gPA[idx_u(s, k, j)];
                         else if (cold) P.s_u[ou + e] = T(0);
                     }
             }
@@ -638,7 +678,7 @@ struct GpiPlan {
 template <typename T, int NX, int NU, int L>
 inline void gpi_consider(int N, int max_smem, GpiPlan &best) {
     if constexpr (gpi_feasible<T, NX, NU, L>()) {
-        using Cfg = GpiCfg<NX, NU, L>;
+        using Cfg = GpiCfg<NX, NU, L, (int)sizeof(T)>;
         const size_t per_warp = Cfg::warp_elems(N) * sizeof(T);
         // the TMA staging area must fit inside the first warp's region
         const size_t blob = (size_t)(3 * NX * NX + 2 * NX * NU + NU * NU + 4 * NX + 2 * NU) * sizeof(T) + 32;

@@ -156,8 +156,10 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
     }
 
     // per-lane matrix rows (registers)
-    T mAmBKt[RX][NX], mKt[RX][NU], mA[RX][NX], mB[RX][NU], vQd[RX], vAPf[RX], vf[RX];
-    T mBt[RU][NX], mQuu[RU][NU], mK[RU][NX], vRd[RU], vBPf[RU];
+    // stage-1 rows (dot with the gathered nx-vector): backward = [AmBKt rows ; B^T rows], forward = [A rows ; Kinf rows]
+    T mS1b[RX + RU][NX], mS1f[RX + RU][NX];
+    T mKt[RX][NU], mB[RX][NU], vQd[RX], vAPf[RX], vf[RX];
+    T mQuu[RU][NU], vRd[RU], vBPf[RU];
     bool xv[RX], uv[RU];  // row validity (padding rows compute zeros)
 #pragma unroll
     for (int a = 0; a < RX; ++a) {
@@ -166,8 +168,8 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
         const int ii = xv[a] ? i : 0;
 #pragma unroll
         for (int m = 0; m < NX; ++m) {
-            mAmBKt[a][m] = xv[a] ? stage[OFF_AMBKT + ii + NX * m] : T(0);
-            mA[a][m] = xv[a] ? stage[OFF_A + ii + NX * m] : T(0);
+            mS1b[a][m] = xv[a] ? stage[OFF_AMBKT + ii + NX * m] : T(0);
+            mS1f[a][m] = xv[a] ? stage[OFF_A + ii + NX * m] : T(0);
         }
 #pragma unroll
         for (int j = 0; j < NU; ++j) {
@@ -185,8 +187,8 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
         const int jj = uv[b] ? j : 0;
 #pragma unroll
         for (int m = 0; m < NX; ++m) {
-            mBt[b][m] = uv[b] ? stage[OFF_B + m + NX * jj] : T(0);  // B^T(j,m) = B(m,j)
-            mK[b][m] = uv[b] ? stage[OFF_K + jj + NU * m] : T(0);
+            mS1b[RX + b][m] = uv[b] ? stage[OFF_B + m + NX * jj] : T(0);  // B^T(j,m) = B(m,j)
+            mS1f[RX + b][m] = uv[b] ? stage[OFF_K + jj + NU * m] : T(0);
         }
 #pragma unroll
         for (int m = 0; m < NU; ++m) mQuu[b][m] = uv[b] ? stage[OFF_QUU + jj + NU * m] : T(0);
@@ -263,15 +265,18 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
     const bool tvb = P.bounds_tv != 0;
     const bool enx = P.en_state_bound != 0, enu = P.en_input_bound != 0;
     T loX[RX], hiX[RX], loU[RU], hiU[RU];  // bounds of this lane's rows (reloaded per k only if time-varying)
+    // a disabled bound (en_*_bound = 0) or a padding row is (-inf, +inf): the clamp is then the identity on every
+    // non-NaN value, so it can stay unconditional in the hot loop
+    const T kInf = (T)INFINITY;
 #pragma unroll
     for (int a = 0; a < RX; ++a) {
-        loX[a] = (enx && xv[a]) ? __ldg(P.x_min + l * RX + a) : T(0);
-        hiX[a] = (enx && xv[a]) ? __ldg(P.x_max + l * RX + a) : T(0);
+        loX[a] = (enx && xv[a]) ? __ldg(P.x_min + l * RX + a) : -kInf;
+        hiX[a] = (enx && xv[a]) ? __ldg(P.x_max + l * RX + a) : kInf;
     }
 #pragma unroll
     for (int b = 0; b < RU; ++b) {
-        loU[b] = (enu && uv[b]) ? __ldg(P.u_min + l * RU + b) : T(0);
-        hiU[b] = (enu && uv[b]) ? __ldg(P.u_max + l * RU + b) : T(0);
+        loU[b] = (enu && uv[b]) ? __ldg(P.u_min + l * RU + b) : -kInf;
+        hiU[b] = (enu && uv[b]) ? __ldg(P.u_max + l * RU + b) : kInf;
     }
     const bool keep_v = (P.s_v != nullptr) || (P.s_z != nullptr);
     // where element (k, row i) of instance-slot s lives inside a pack region
@@ -366,59 +371,37 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
 #pragma unroll
             for (int a = 0; a < RX; ++a) xo[a] = x0o[a];
             gather_x(xo, Xf);
-            T pa[PVP], pb[PVP], dc[RU];  // state of the current column (prefetched)
-            load_pack(aPA, 0, pa);
-            load_pack(aPB, 0, pb);
-#pragma unroll
-            for (int b = 0; b < RU; ++b) dc[b] = lds(aD + (unsigned)(b * 32) * ES, T());
-            for (int k = 0; k < N; ++k) {
-                // prefetch the next column's state while this one is being processed (indices clamped: always valid)
-                T pan[PVP], pbn[PVP], dn_[RU];
-                const int kx = (k + 1 < N) ? k + 1 : k, ku = (k + 2 < N) ? k + 1 : ((N >= 2) ? N - 2 : 0);
-                load_pack(aPA, kx, pan);
-                load_pack(aPB, kx, pbn);
-#pragma unroll
-                for (int b = 0; b < RU; ++b) dn_[b] = lds(aD + (unsigned)ku * DSTR + (unsigned)(b * 32) * ES, T());
-                if (tvb) {
-#pragma unroll
-                    for (int a = 0; a < RX; ++a) {
-                        loX[a] = (enx && xv[a]) ? __ldg(P.x_min + (int64_t)k * NX + l * RX + a) : T(0);
-                        hiX[a] = (enx && xv[a]) ? __ldg(P.x_max + (int64_t)k * NX + l * RX + a) : T(0);
-                    }
-                    if (k < N - 1) {
-#pragma unroll
-                        for (int b = 0; b < RU; ++b) {
-                            loU[b] = (enu && uv[b]) ? __ldg(P.u_min + (int64_t)k * NU + l * RU + b) : T(0);
-                            hiU[b] = (enu && uv[b]) ? __ldg(P.u_max + (int64_t)k * NU + l * RU + b) : T(0);
-                        }
-                    }
-                }
-                T u[RU], Uf[NU];
-                if (k < N - 1) {
-#pragma unroll
-                    for (int b = 0; b < RU; ++b) {  // u_k = -(Kinf x_k) - d_k
-                        T t = mK[b][0] * Xf[0];
-#pragma unroll
-                        for (int m = 1; m < NX; ++m) t = mac<FAST>(t, mK[b][m], Xf[m]);
-                        u[b] = (-t) - dc[b];
-                    }
-                    gather_u(u, Uf);
-                }
-                T na[PVP], nb[PVP];  // new packs of this column
+            // one column: slack + dual update of this lane's rows, residual maxima; HASU = the column has inputs
+            auto column = [&](int k, const bool HASU, const T (&u)[RU]) {  // always inlined with a literal HASU
+                T pa[PVP], pb[PVP], na[PVP], nb[PVP];
+                load_pack(aPA, k, pa);
+                load_pack(aPB, k, pb);
 #pragma unroll
                 for (int e = 0; e < PVP; ++e) {
                     na[e] = pa[e];
                     nb[e] = pb[e];
                 }
-                // state column k: vnew = clamp(x + g), g += x - vnew
+                if (tvb) {
 #pragma unroll
-                for (int a = 0; a < RX; ++a) {
+                    for (int a = 0; a < RX; ++a) {
+                        loX[a] = (enx && xv[a]) ? __ldg(P.x_min + (int64_t)k * NX + l * RX + a) : loX[a];
+                        hiX[a] = (enx && xv[a]) ? __ldg(P.x_max + (int64_t)k * NX + l * RX + a) : hiX[a];
+                    }
+                    if (HASU) {
+#pragma unroll
+                        for (int b = 0; b < RU; ++b) {
+                            loU[b] = (enu && uv[b]) ? __ldg(P.u_min + (int64_t)k * NU + l * RU + b) : loU[b];
+                            hiU[b] = (enu && uv[b]) ? __ldg(P.u_max + (int64_t)k * NU + l * RU + b) : hiU[b];
+                        }
+                    }
+                }
+#pragma unroll
+                for (int a = 0; a < RX; ++a) {  // vnew = clamp(x + g), g += x - vnew
                     T vo = pa[a];
                     if constexpr (SLOW) {
                         if (vin) vo = (P.s_v && xv[a]) ? P.s_v[offx + (int64_t)k * NX + l * RX + a] : T(0);
                     }
-                    T v = xo[a] + pb[a];
-                    if (enx) v = clamp_box<FAST>(v, loX[a], hiX[a]);
+                    const T v = clamp_box<FAST>(xo[a] + pb[a], loX[a], hiX[a]);
                     na[a] = v;
                     nb[a] = (pb[a] + xo[a]) - v;
                     if constexpr (SLOW) {
@@ -427,15 +410,14 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
                     rpx = absmax(rpx, xo[a] - v);
                     rdx = absmax(rdx, vo - v);
                 }
-                if (k < N - 1) {
+                if (HASU) {
 #pragma unroll
                     for (int b = 0; b < RU; ++b) {
                         T zo = pa[RX + b];
                         if constexpr (SLOW) {
                             if (vin) zo = (P.s_z && uv[b]) ? P.s_z[offu + (int64_t)k * NU + l * RU + b] : T(0);
                         }
-                        T z = u[b] + pb[RX + b];
-                        if (enu) z = clamp_box<FAST>(z, loU[b], hiU[b]);
+                        const T z = clamp_box<FAST>(u[b] + pb[RX + b], loU[b], hiU[b]);
                         na[RX + b] = z;
                         nb[RX + b] = (pb[RX + b] + u[b]) - z;
                         if constexpr (SLOW) {
@@ -449,27 +431,27 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
                     store_pack(aPA, k, na);
                     store_pack(aPB, k, nb);
                 }
-                if (k < N - 1) {
-                    // x_{k+1} = (A x_k + B u_k) + f
+            };
+            for (int k = 0; k < N - 1; ++k) {
+                T u[RU], Uf[NU], t1[RX + RU], bu[RX];
+                dots<FAST>(mS1f, Xf, t1);  // [A x_k ; Kinf x_k]
 #pragma unroll
-                    for (int a = 0; a < RX; ++a) {
-                        T ax = mA[a][0] * Xf[0];
-#pragma unroll
-                        for (int m = 1; m < NX; ++m) ax = mac<FAST>(ax, mA[a][m], Xf[m]);
-                        T bu = mB[a][0] * Uf[0];
-#pragma unroll
-                        for (int j = 1; j < NU; ++j) bu = mac<FAST>(bu, mB[a][j], Uf[j]);
-                        xo[a] = (ax + bu) + vf[a];
-                    }
-                    gather_x(xo, Xf);
+                for (int b = 0; b < RU; ++b) {  // u_k = -(Kinf x_k) - d_k
+                    const T d = lds(aD + (unsigned)k * DSTR + (unsigned)(b * 32) * ES, T());
+                    u[b] = (-t1[RX + b]) - d;
                 }
+                gather_u(u, Uf);
+                column(k, true, u);
+                dots<FAST>(mB, Uf, bu);
 #pragma unroll
-                for (int e = 0; e < PVP; ++e) {
-                    pa[e] = pan[e];
-                    pb[e] = pbn[e];
-                }
+                for (int a = 0; a < RX; ++a) xo[a] = (t1[a] + bu[a]) + vf[a];  // x_{k+1} = (A x_k + B u_k) + f
+                gather_x(xo, Xf);
+            }
+            {
+                T udummy[RU];
 #pragma unroll
-                for (int b = 0; b < RU; ++b) dc[b] = dn_[b];
+                for (int b = 0; b < RU; ++b) udummy[b] = T(0);
+                column(N - 1, false, udummy);
             }
         };
 
@@ -501,34 +483,20 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
                     gather_u(rn, Rn);
                 }
                 // d_k = Quu_inv ((B^T p_{k+1} + r_k) + BPf)
-                T s[RU], Sf[NU];
+                T s[RU], Sf[NU], acc1[RX + RU], kr[RX], dq[RU];
+                dots<FAST>(mS1b, Pf, acc1);  // [AmBKt p_{k+1} ; B^T p_{k+1}]
 #pragma unroll
-                for (int b = 0; b < RU; ++b) {
-                    T t = mBt[b][0] * Pf[0];
-#pragma unroll
-                    for (int m = 1; m < NX; ++m) t = mac<FAST>(t, mBt[b][m], Pf[m]);
-                    s[b] = (t + r[b]) + vBPf[b];
-                }
+                for (int b = 0; b < RU; ++b) s[b] = (acc1[RX + b] + r[b]) + vBPf[b];
                 gather_u(s, Sf);
                 // p_k = ((q_k + AmBKt p_{k+1}) - Kinf^T r_k) + APf
+                dots<FAST>(mKt, Rf, kr);
 #pragma unroll
-                for (int a = 0; a < RX; ++a) {
-                    T acc = mAmBKt[a][0] * Pf[0];
-#pragma unroll
-                    for (int m = 1; m < NX; ++m) acc = mac<FAST>(acc, mAmBKt[a][m], Pf[m]);
-                    T kr = mKt[a][0] * Rf[0];
-#pragma unroll
-                    for (int j = 1; j < NU; ++j) kr = mac<FAST>(kr, mKt[a][j], Rf[j]);
-                    po[a] = ((q[a] + acc) - kr) + vAPf[a];
-                }
+                for (int a = 0; a < RX; ++a) po[a] = ((q[a] + acc1[a]) - kr[a]) + vAPf[a];
                 gather_x(po, Pf);
+                dots<FAST>(mQuu, Sf, dq);
 #pragma unroll
-                for (int b = 0; b < RU; ++b) {
-                    T t = mQuu[b][0] * Sf[0];
-#pragma unroll
-                    for (int m = 1; m < NU; ++m) t = mac<FAST>(t, mQuu[b][m], Sf[m]);
-                    if (active && uv[b]) sts(aD + (unsigned)k * DSTR + (unsigned)(b * 32) * ES, t);
-                }
+                for (int b = 0; b < RU; ++b)
+                    if (active && uv[b]) sts(aD + (unsigned)k * DSTR + (unsigned)(b * 32) * ES, dq[b]);
 #pragma unroll
                 for (int a = 0; a < RX; ++a) q[a] = qn[a];
 #pragma unroll
@@ -618,27 +586,18 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
 #pragma unroll
                 for (int a = 0; a < RX; ++a) na[a] = xo[a];
                 if (k < N - 1) {
-                    T u[RU], Uf[NU];
+                    T u[RU], Uf[NU], t1[RX + RU], bu[RX];
+                    dots<FAST>(mS1f, Xf, t1);
 #pragma unroll
                     for (int b = 0; b < RU; ++b) {
                         const T d = lds(aD + (unsigned)k * DSTR + (unsigned)(b * 32) * ES, T());
-                        T t = mK[b][0] * Xf[0];
-#pragma unroll
-                        for (int m = 1; m < NX; ++m) t = mac<FAST>(t, mK[b][m], Xf[m]);
-                        u[b] = (-t) - d;
+                        u[b] = (-t1[RX + b]) - d;
                         na[RX + b] = u[b];
                     }
                     gather_u(u, Uf);
+                    dots<FAST>(mB, Uf, bu);
 #pragma unroll
-                    for (int a = 0; a < RX; ++a) {
-                        T ax = mA[a][0] * Xf[0];
-#pragma unroll
-                        for (int m = 1; m < NX; ++m) ax = mac<FAST>(ax, mA[a][m], Xf[m]);
-                        T bu = mB[a][0] * Uf[0];
-#pragma unroll
-                        for (int j = 1; j < NU; ++j) bu = mac<FAST>(bu, mB[a][j], Uf[j]);
-                        xo[a] = (ax + bu) + vf[a];
-                    }
+                    for (int a = 0; a < RX; ++a) xo[a] = (t1[a] + bu[a]) + vf[a];
                 }
                 store_pack(aPA, k, na);
                 if (k < N - 1) gather_x(xo, Xf);

@@ -119,6 +119,7 @@ struct tinympc_b200_solver {
     const tmpc::DimEntry *dim = nullptr;
     // host copies (native dtype, column-major)
     std::vector<char> A, Bm, f, Qd, Rd, Kinf, Pinf, Quu, AmBKt, APf, BPf;
+    std::vector<char> h_xlo, h_xhi, h_ulo, h_uhi;  // column 0 of the bounds
     bool has_xb = false, has_ub = false;
     int ncx = 0, ncu = 0, nlx = 0, nlu = 0, ntvx = 0, ntvu = 0;
     int cone_x_start[4] = {0, 0, 0, 0}, cone_u_start[4] = {0, 0, 0, 0};
@@ -263,6 +264,8 @@ void base_desc(const tinympc_b200_solver *s, tmpc::LaunchDesc &d, const Features
     d.tv_Alin_x = s->d_tvA_x.p; d.tv_blin_x = s->d_tvb_x.p; d.tv_Alin_u = s->d_tvA_u.p; d.tv_blin_u = s->d_tvb_u.p;
     d.gmat = s->d_blob.p;
     d.bounds_tv = s->bounds_tv;
+    d.h_xlo = s->h_xlo.empty() ? nullptr : s->h_xlo.data(); d.h_xhi = s->h_xhi.empty() ? nullptr : s->h_xhi.data();
+    d.h_ulo = s->h_ulo.empty() ? nullptr : s->h_ulo.data(); d.h_uhi = s->h_uhi.empty() ? nullptr : s->h_uhi.data();
     d.sm_count = s->sm_count;
     d.max_smem_optin = s->max_smem_optin;
 }
@@ -498,10 +501,12 @@ int tinympc_b200_create(const tinympc_problem_t *p, int32_t device, tinympc_b200
     if (p->x_min && p->x_max) {
         ok &= !upload(s->d_xmin, p->x_min, es * nx * N) && !upload(s->d_xmax, p->x_max, es * nx * N);
         s->has_xb = true;
+        s->h_xlo = copy_bytes(p->x_min, es * nx); s->h_xhi = copy_bytes(p->x_max, es * nx);
     }
     if (p->u_min && p->u_max) {
         ok &= !upload(s->d_umin, p->u_min, es * nu * (N - 1)) && !upload(s->d_umax, p->u_max, es * nu * (N - 1));
         s->has_ub = true;
+        s->h_ulo = copy_bytes(p->u_min, es * nu); s->h_uhi = copy_bytes(p->u_max, es * nu);
     }
     auto rd = [&](const void *base, int i) { return p->dtype == TINYMPC_F64 ? ((const double *)base)[i] : (double)((const float *)base)[i]; };
     s->ncx = p->num_state_cones; s->ncu = p->num_input_cones;

@@ -83,6 +83,40 @@ __device__ __forceinline__ void dots(const double (&M)[NR][NE], const double (&v
     }
 }
 
+// same, with the coefficients supplied by a callable coef(r, k) (e.g. constant-bank matrix entries in the TPI kernel)
+template <bool FAST, int NR, int NE, typename F>
+__device__ __forceinline__ void dots_f(F coef, const float (&v)[NE], float (&out)[NR]) {
+#pragma unroll
+    for (int r = 0; r + 1 < NR; r += 2) {
+        unsigned long long acc = pack2(coef(r, 0) * v[0], coef(r + 1, 0) * v[0]);
+#pragma unroll
+        for (int k = 1; k < NE; ++k) {
+            if constexpr (FAST) {
+                acc = fma2(pack2(coef(r, k), coef(r + 1, k)), pack2(v[k], v[k]), acc);
+            } else {
+                acc = add2(acc, pack2(coef(r, k) * v[k], coef(r + 1, k) * v[k]));
+            }
+        }
+        unpack2(acc, out[r], out[r + 1]);
+    }
+    if constexpr (NR % 2 == 1) {
+        float s = coef(NR - 1, 0) * v[0];
+#pragma unroll
+        for (int k = 1; k < NE; ++k) s = mac<FAST>(s, coef(NR - 1, k), v[k]);
+        out[NR - 1] = s;
+    }
+}
+template <bool FAST, int NR, int NE, typename F>
+__device__ __forceinline__ void dots_f(F coef, const double (&v)[NE], double (&out)[NR]) {
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        double s = coef(r, 0) * v[0];
+#pragma unroll
+        for (int k = 1; k < NE; ++k) s = mac<FAST>(s, coef(r, k), v[k]);
+        out[r] = s;
+    }
+}
+
 template <typename T>
 __device__ __forceinline__ T tabs(T a) {
     return a < T(0) ? -a : a;
@@ -154,6 +188,7 @@ struct KParams {
     int64_t Bpad;  // workspace stride (instances, multiple of 32)
     int cold;
     int bounds_tv;      // bounds vary along the horizon (else row 0 is used for every k)
+    T xlo[NX], xhi[NX], ulo[NU], uhi[NU];  // time-invariant bounds (column 0); (-inf, +inf) when the bound is disabled
     const T *Pinf_g;    // Pinf in global memory (column-major), GPI terminal cost
     int xref_pi, uref_pi;
     // inputs (user layout, instance-major)

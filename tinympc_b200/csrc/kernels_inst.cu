@@ -3,6 +3,7 @@
 // and exports one type-erased launcher  tm_dim_entry_<nx>_<nu>().
 #include <algorithm>
 #include <cstring>
+#include <limits>
 
 #include "launch.h"
 #include "tpi_kernel.cuh"
@@ -54,6 +55,17 @@ void fill_params(KParams<T, TM_NX, TM_NU> &P, const LaunchDesc &d) {
     P.Bpad = d.Bpad;
     P.cold = io.cold_start;
     P.bounds_tv = d.bounds_tv;
+    {
+        const T inf = std::numeric_limits<T>::infinity();
+        for (int i = 0; i < NX; ++i) {
+            P.xlo[i] = (d.en_state_bound && d.h_xlo) ? ((const T *)d.h_xlo)[i] : -inf;
+            P.xhi[i] = (d.en_state_bound && d.h_xhi) ? ((const T *)d.h_xhi)[i] : inf;
+        }
+        for (int j = 0; j < NU; ++j) {
+            P.ulo[j] = (d.en_input_bound && d.h_ulo) ? ((const T *)d.h_ulo)[j] : -inf;
+            P.uhi[j] = (d.en_input_bound && d.h_uhi) ? ((const T *)d.h_uhi)[j] : inf;
+        }
+    }
     P.Pinf_g = d.gmat ? (const T *)d.gmat + (NX * NX + NX * NU + NX + NX + NU + NU * NX) : nullptr;
     P.xref_pi = io.xref_per_instance;
     P.uref_pi = io.uref_per_instance;

@@ -260,13 +260,10 @@ __global__ void __launch_bounds__(TPI_THREADS, (sizeof(T) == 4 && !EXT) ? 4 : 2)
             T xr[NX], vn[NX], g[NX];
             load_col<T, NX>(xrefp + (int64_t)(N - 1) * NX, xr);
             if (zin) { zero(vn); zero(g); } else { SX::load(P.w_v[c], N - 1, S, b, vn); SX::load(P.w_g, N - 1, S, b, g); }
+            T pt[NX];
+            dots_f<FAST, NX, NX>([&](int j, int i) { return P.Pinf[i + NX * j]; }, xr, pt);  // (Pinf^T xref)(j), i ascending
 #pragma unroll
-            for (int j = 0; j < NX; ++j) {
-                T s = xr[0] * P.Pinf[0 + NX * j];
-#pragma unroll
-                for (int i = 1; i < NX; ++i) s = mac<FAST>(s, xr[i], P.Pinf[i + NX * j]);
-                p[j] = nmac<FAST>(-s, rho, vn[j] - g[j]);
-            }
+            for (int j = 0; j < NX; ++j) p[j] = nmac<FAST>(-pt[j], rho, vn[j] - g[j]);
             if constexpr (EXT) {
                 if (P.soc_x) {
                     SX::load(P.w_vc, N - 1, S, b, vn); SX::load(P.w_gc, N - 1, S, b, g);
@@ -338,36 +335,18 @@ __global__ void __launch_bounds__(TPI_THREADS, (sizeof(T) == 4 && !EXT) ? 4 : 2)
                 }
             }
             // d_k = Quu_inv * ((B^T p_{k+1} + r_k) + BPf)                                (admm.cpp:17)
-            T s[NU], d[NU];
+            T s[NU], d[NU], tb[NU];
+            dots_f<FAST, NU, NX>([&](int j, int i) { return P.Bm[i + NX * j]; }, p, tb);  // B^T p
 #pragma unroll
-            for (int j = 0; j < NU; ++j) {
-                T t = P.Bm[0 + NX * j] * p[0];
-#pragma unroll
-                for (int i = 1; i < NX; ++i) t = mac<FAST>(t, P.Bm[i + NX * j], p[i]);
-                s[j] = (t + r[j]) + P.BPf[j];
-            }
-#pragma unroll
-            for (int j = 0; j < NU; ++j) {
-                T t = P.Quu[j + NU * 0] * s[0];
-#pragma unroll
-                for (int m = 1; m < NU; ++m) t = mac<FAST>(t, P.Quu[j + NU * m], s[m]);
-                d[j] = t;
-            }
+            for (int j = 0; j < NU; ++j) s[j] = (tb[j] + r[j]) + P.BPf[j];
+            dots_f<FAST, NU, NU>([&](int j, int m) { return P.Quu[j + NU * m]; }, s, d);
             SU::store(P.w_d, k, S, b, d);
             // p_k = ((q_k + AmBKt p_{k+1}) - Kinf^T r_k) + APf                             (admm.cpp:18)
-            T pn[NX];
+            T pa_[NX], kr[NX];
+            dots_f<FAST, NX, NX>([&](int i, int m) { return P.AmBKt[i + NX * m]; }, p, pa_);
+            dots_f<FAST, NX, NU>([&](int i, int j) { return P.Kinf[j + NU * i]; }, r, kr);
 #pragma unroll
-            for (int i = 0; i < NX; ++i) {
-                T a = P.AmBKt[i + NX * 0] * p[0];
-#pragma unroll
-                for (int m = 1; m < NX; ++m) a = mac<FAST>(a, P.AmBKt[i + NX * m], p[m]);
-                T kr = P.Kinf[0 + NU * i] * r[0];
-#pragma unroll
-                for (int j = 1; j < NU; ++j) kr = mac<FAST>(kr, P.Kinf[j + NU * i], r[j]);
-                pn[i] = ((q[i] + a) - kr) + P.APf[i];
-            }
-#pragma unroll
-            for (int i = 0; i < NX; ++i) p[i] = pn[i];
+            for (int i = 0; i < NX; ++i) p[i] = ((q[i] + pa_[i]) - kr[i]) + P.APf[i];
         }
 
         // ---- forward_pass fused with update_slack, update_dual, residuals ----
@@ -379,16 +358,20 @@ __global__ void __launch_bounds__(TPI_THREADS, (sizeof(T) == 4 && !EXT) ? 4 : 2)
             {   // state column k
                 T g[NX], vo[NX], vn[NX];
                 if (zin) { zero(g); zero(vo); } else { SX::load(P.w_g, k, S, b, g); SX::load(P.w_v[vs], k, S, b, vo); }
+                auto upd_x = [&](auto lo, auto hi) {  // vnew = clamp(x + g); g += x - vnew; residual maxima
 #pragma unroll
-                for (int i = 0; i < NX; ++i) {
-                    T v = x[i] + g[i];
-                    if (P.en_state_bound) v = clamp_ref(v, __ldg(P.x_min + (int64_t)k * NX + i), __ldg(P.x_max + (int64_t)k * NX + i));
-                    vn[i] = v;
-                    g[i] = (g[i] + x[i]) - v;
-                    const T e1 = tabs(x[i] - v), e2 = tabs(vo[i] - v);
-                    rpx = (e1 > rpx) ? e1 : rpx;
-                    rdx = (e2 > rdx) ? e2 : rdx;
-                }
+                    for (int i = 0; i < NX; ++i) {
+                        const T v = FAST ? fmin(fmax(x[i] + g[i], lo(i)), hi(i)) : clamp_ref(x[i] + g[i], lo(i), hi(i));
+                        vn[i] = v;
+                        g[i] = (g[i] + x[i]) - v;
+                        rpx = fmax(rpx, tabs(x[i] - v));  // == (|d| > m) ? |d| : m  (m is never NaN)
+                        rdx = fmax(rdx, tabs(vo[i] - v));
+                    }
+                };
+                if (P.bounds_tv && P.en_state_bound)
+                    upd_x([&](int i) { return __ldg(P.x_min + (int64_t)k * NX + i); }, [&](int i) { return __ldg(P.x_max + (int64_t)k * NX + i); });
+                else
+                    upd_x([&](int i) { return P.xlo[i]; }, [&](int i) { return P.xhi[i]; });  // constant-bank operands; (-inf,+inf) if disabled
                 SX::store(P.w_v[dst], k, S, b, vn);
                 SX::store(P.w_g, k, S, b, g);
                 if constexpr (EXT) {
@@ -431,23 +414,26 @@ __global__ void __launch_bounds__(TPI_THREADS, (sizeof(T) == 4 && !EXT) ? 4 : 2)
                 T d[NU], y[NU], zo[NU], u[NU], zn[NU];
                 SU::load(P.w_d, k, S, b, d);
                 if (zin) { zero(y); zero(zo); } else { SU::load(P.w_y, k, S, b, y); SU::load(P.w_z[vs], k, S, b, zo); }
+                {   // u_k = -(Kinf x_k) - d_k                                              (admm.cpp:29)
+                    T kx[NU];
+                    dots_f<FAST, NU, NX>([&](int j, int m) { return P.Kinf[j + NU * m]; }, x, kx);
 #pragma unroll
-                for (int j = 0; j < NU; ++j) {  // u_k = -(Kinf x_k) - d_k                   (admm.cpp:29)
-                    T t = P.Kinf[j + NU * 0] * x[0];
-#pragma unroll
-                    for (int m = 1; m < NX; ++m) t = mac<FAST>(t, P.Kinf[j + NU * m], x[m]);
-                    u[j] = (-t) - d[j];
+                    for (int j = 0; j < NU; ++j) u[j] = (-kx[j]) - d[j];
                 }
+                auto upd_u = [&](auto lo, auto hi) {
 #pragma unroll
-                for (int j = 0; j < NU; ++j) {
-                    T z = u[j] + y[j];
-                    if (P.en_input_bound) z = clamp_ref(z, __ldg(P.u_min + (int64_t)k * NU + j), __ldg(P.u_max + (int64_t)k * NU + j));
-                    zn[j] = z;
-                    y[j] = (y[j] + u[j]) - z;
-                    const T e1 = tabs(u[j] - z), e2 = tabs(zo[j] - z);
-                    rpu = (e1 > rpu) ? e1 : rpu;
-                    rdu = (e2 > rdu) ? e2 : rdu;
-                }
+                    for (int j = 0; j < NU; ++j) {
+                        const T z = FAST ? fmin(fmax(u[j] + y[j], lo(j)), hi(j)) : clamp_ref(u[j] + y[j], lo(j), hi(j));
+                        zn[j] = z;
+                        y[j] = (y[j] + u[j]) - z;
+                        rpu = fmax(rpu, tabs(u[j] - z));
+                        rdu = fmax(rdu, tabs(zo[j] - z));
+                    }
+                };
+                if (P.bounds_tv && P.en_input_bound)
+                    upd_u([&](int j) { return __ldg(P.u_min + (int64_t)k * NU + j); }, [&](int j) { return __ldg(P.u_max + (int64_t)k * NU + j); });
+                else
+                    upd_u([&](int j) { return P.ulo[j]; }, [&](int j) { return P.uhi[j]; });
                 SU::store(P.w_z[dst], k, S, b, zn);
                 SU::store(P.w_y, k, S, b, y);
                 if constexpr (EXT) {
@@ -486,19 +472,11 @@ __global__ void __launch_bounds__(TPI_THREADS, (sizeof(T) == 4 && !EXT) ? 4 : 2)
                     }
                 }
                 // x_{k+1} = (A x_k + B u_k) + f                                            (admm.cpp:30)
-                T xn[NX];
+                T ax[NX], bu[NX];
+                dots_f<FAST, NX, NX>([&](int i, int m) { return P.A[i + NX * m]; }, x, ax);
+                dots_f<FAST, NX, NU>([&](int i, int j) { return P.Bm[i + NX * j]; }, u, bu);
 #pragma unroll
-                for (int i = 0; i < NX; ++i) {
-                    T ax = P.A[i + NX * 0] * x[0];
-#pragma unroll
-                    for (int m = 1; m < NX; ++m) ax = mac<FAST>(ax, P.A[i + NX * m], x[m]);
-                    T bu = P.Bm[i + NX * 0] * u[0];
-#pragma unroll
-                    for (int j = 1; j < NU; ++j) bu = mac<FAST>(bu, P.Bm[i + NX * j], u[j]);
-                    xn[i] = (ax + bu) + P.f[i];
-                }
-#pragma unroll
-                for (int i = 0; i < NX; ++i) x[i] = xn[i];
+                for (int i = 0; i < NX; ++i) x[i] = (ax[i] + bu[i]) + P.f[i];
             }
         }
         it_done = it + 1;
@@ -598,27 +576,15 @@ __global__ void __launch_bounds__(TPI_THREADS, (sizeof(T) == 4 && !EXT) ? 4 : 2)
             if (k < N - 1 && ran) {
                 T d[NU], u[NU];
                 SU::load(P.w_d, k, S, b, d);
+                T kx[NU], ax[NX], bu[NX];
+                dots_f<FAST, NU, NX>([&](int j, int m) { return P.Kinf[j + NU * m]; }, x, kx);
 #pragma unroll
-                for (int j = 0; j < NU; ++j) {
-                    T t = P.Kinf[j + NU * 0] * x[0];
-#pragma unroll
-                    for (int m = 1; m < NX; ++m) t = mac<FAST>(t, P.Kinf[j + NU * m], x[m]);
-                    u[j] = (-t) - d[j];
-                }
+                for (int j = 0; j < NU; ++j) u[j] = (-kx[j]) - d[j];
                 if (P.s_u) store_col<T, NU>(P.s_u + offu + (int64_t)k * NU, u);
-                T xn[NX];
+                dots_f<FAST, NX, NX>([&](int i, int m) { return P.A[i + NX * m]; }, x, ax);
+                dots_f<FAST, NX, NU>([&](int i, int j) { return P.Bm[i + NX * j]; }, u, bu);
 #pragma unroll
-                for (int i = 0; i < NX; ++i) {
-                    T ax = P.A[i + NX * 0] * x[0];
-#pragma unroll
-                    for (int m = 1; m < NX; ++m) ax = mac<FAST>(ax, P.A[i + NX * m], x[m]);
-                    T bu = P.Bm[i + NX * 0] * u[0];
-#pragma unroll
-                    for (int j = 1; j < NU; ++j) bu = mac<FAST>(bu, P.Bm[i + NX * j], u[j]);
-                    xn[i] = (ax + bu) + P.f[i];
-                }
-#pragma unroll
-                for (int i = 0; i < NX; ++i) x[i] = xn[i];
+                for (int i = 0; i < NX; ++i) x[i] = (ax[i] + bu[i]) + P.f[i];
             } else if (k < N - 1 && P.s_u && cold) {
                 T a[NU];
                 zero(a);

@@ -272,3 +272,51 @@ def test_device_resident_closed_loop_matches_oracle(kernel):
             nxt[:, i] = (ax + bu) + f[i]
         x0 = nxt
         assert H.bits_equal(loop.x0.cpu().numpy(), x0), ("advance", k)
+
+
+@pytest.mark.parametrize("kernel", ["tpi", "gpi"])
+@pytest.mark.parametrize("dims", [(4, 2), (4, 8), (6, 3), (8, 8), (12, 2), (12, 8), (16, 2), (16, 4), (16, 8)])
+def test_every_compiled_dimension_vs_oracle(dims, kernel):
+    """Random LTI problems for the other compiled (nx, nu) pairs (lane mappings L=4 and L=8, padding rows),
+    fixed work and to-convergence, fp32, against the oracle on every scalar."""
+    nx, nu = dims
+    dt = np.float32
+    for N, B in ((10, 70), (33, 41)):
+        spec = wl.random_lti(nx, nu, N, seed=nx * 10 + nu)
+        prob = setup_problem(spec, dt)
+        st = abi.Settings.from_buffer_copy(spec.settings)
+        st.max_iter = 30
+        inst = wl.random_instances(B, nx, N, seed=N, dtype=dt)
+        inst["x0"] = (3.0 * inst["x0"]).astype(dt)  # large enough for the input bounds to bite
+        solver = _mk_solver(prob, st, kernel)
+        want = tuple(H.BOX_STATE)
+        g = solver.solve(inst["x0"], inst["Xref"], None, cold_start=True, want_state=want)
+        o = _port(prob, st, inst["x0"], inst["Xref"], None, None, True, want)
+        for key in H.OUT_KEYS + H.BOX_STATE:
+            assert H.bits_equal(g[key], o[key]), (dims, N, key)
+        assert (np.abs(o["znew"]) >= 1.0 - 1e-6).any()  # the box was active somewhere
+
+
+@pytest.mark.parametrize("kernel", ["tpi", "gpi"])
+def test_time_varying_bounds(kernel):
+    """Bounds are full nx x N / nu x (N-1) matrices in the reference API (types.hpp:117-120); every example passes
+    constants, here they really vary along the horizon."""
+    spec = wl.quadrotor(N=20)
+    dt = np.float32
+    rng = np.random.default_rng(3)
+    N = spec.N
+    cons = dict(spec.constraints)
+    cons["x_min"] = (-5.0 - rng.uniform(0, 1, (12, N))).astype(dt)
+    cons["x_max"] = (5.0 + rng.uniform(0, 1, (12, N))).astype(dt)
+    cons["u_min"] = (-0.5 + 0.3 * rng.uniform(0, 1, (4, N - 1))).astype(dt)
+    cons["u_max"] = (0.5 - 0.3 * rng.uniform(0, 1, (4, N - 1))).astype(dt)
+    spec.constraints = cons
+    prob = setup_problem(spec, dt)
+    st = spec.settings
+    inst = wl.tracking_instances(90, N=N, seed=4, dtype=dt)
+    solver = _mk_solver(prob, st, kernel)
+    want = tuple(H.BOX_STATE)
+    g = solver.solve(inst["x0"], inst["Xref"], None, cold_start=True, want_state=want)
+    o = _port(prob, st, inst["x0"], inst["Xref"], None, None, True, want)
+    for key in H.OUT_KEYS + H.BOX_STATE:
+        assert H.bits_equal(g[key], o[key]), key

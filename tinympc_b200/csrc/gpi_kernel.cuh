@@ -261,7 +261,6 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
     };
 
     const bool cold = P.cold != 0;
-    const int64_t ngroups = (P.B + IPW - 1) / IPW;
     const bool tvb = P.bounds_tv != 0;
     const bool enx = P.en_state_bound != 0, enu = P.en_input_bound != 0;
     T loX[RX], hiX[RX], loU[RU], hiU[RU];  // bounds of this lane's rows (reloaded per k only if time-varying)
@@ -283,49 +282,181 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
     auto idx_x = [&](int s, int k, int i) { return (k * 32 + s * L + i / RX) * PVP + (i % RX); };
     auto idx_u = [&](int s, int k, int j) { return (k * 32 + s * L + j / RU) * PVP + RX + (j % RU); };
 
-    for (;;) {
-        // ---- next group of IPW instances ----
-        unsigned long long grp = 0;
-        if (lane == 0) grp = atomicAdd(queue, 1ULL);
-        grp = __shfl_sync(0xffffffffu, grp, 0);
-        if ((int64_t)grp >= ngroups) break;
-        const int64_t inst = (int64_t)grp * IPW + slot;
-        const bool live = inst < P.B;
-        const int64_t bi = live ? inst : (P.B - 1);  // clamp so that every address stays valid
-        const int64_t offx = bi * (int64_t)N * NX, offu = bi * (int64_t)(N - 1) * NU;
-        const T *xrefp = P.Xref + (P.xref_pi ? offx : 0) + l * RX;
-        const T *urefp = P.Uref ? P.Uref + (P.uref_pi ? offu : 0) + l * RU : nullptr;
+    // ---- per-slot bookkeeping (identical in the L lanes of a slot) ----
+    int64_t inst = -1;    // instance held by this lane's slot
+    bool busy = false;    // the slot holds an unfinished instance
+    bool want = true;     // the slot should try to fetch an instance
+    int it = 0, solved = 0;
+    T res_px = T(0), res_dx = T(0), res_pu = T(0), res_du = T(0);
+    T x0o[RX], pterm[RX];
+#pragma unroll
+    for (int a = 0; a < RX; ++a) x0o[a] = pterm[a] = T(0);
+    const T *xrefp = P.Xref + l * RX;
+    const bool has_uref = P.Uref != nullptr;  // warp-uniform: keeps the loops free of divergence bookkeeping
+    const T *urefp = has_uref ? P.Uref + l * RU : P.Xref;
+    int64_t offx = 0, offu = 0;
 
-        // ---- prologue: zero the state (also defines padding slots), then load a warm start ----
+    // linear cost of column k for this lane's rows (update_linear_cost, admm.cpp:266-280):
+    //   q = -(xref*Qd) - rho*(vnew - g),  r = -(uref*Rd) - rho*(znew - y)
+    auto cost = [&](int k, const T *xp, const T *up, T (&q)[RX], T (&r)[RU]) {
+        T pa[PVP], pb[PVP];
+        load_pack(aPA, k, pa);
+        load_pack(aPB, k, pb);
+#pragma unroll
+        for (int a = 0; a < RX; ++a) {
+            const T xr = xv[a] ? __ldg(xp + a) : T(0);
+            q[a] = nmac<FAST>(-(xr * vQd[a]), rho, pa[a] - pb[a]);
+        }
+#pragma unroll
+        for (int b = 0; b < RU; ++b) {
+            const T ur = (has_uref && uv[b]) ? __ldg(up + b) : T(0);
+            r[b] = nmac<FAST>(-(ur * vRd[b]), rho, pa[RX + b] - pb[RX + b]);
+        }
+    };
+
+    // forward pass fused with slack / dual update / residuals.  SLOW = some slot is in the first iteration of a
+    // warm start (work->v / work->z come from the caller) or work->v / work->z are being persisted.
+    auto forward = [&](auto tag, const bool vin, T &rpx, T &rdx, T &rpu, T &rdu) {
+        constexpr bool SLOW = decltype(tag)::value;
+        T xo[RX], Xf[NX];
+#pragma unroll
+        for (int a = 0; a < RX; ++a) xo[a] = x0o[a];
+        gather_x(xo, Xf);
+        // one column: slack + dual update of this lane's rows, residual maxima; HASU = the column has inputs
+        auto column = [&](int k, const bool HASU, const T (&u)[RU]) {  // always inlined with a literal HASU
+            T pa[PVP], pb[PVP], na[PVP], nb[PVP];
+            load_pack(aPA, k, pa);
+            load_pack(aPB, k, pb);
+#pragma unroll
+            for (int e = 0; e < PVP; ++e) {
+                na[e] = pa[e];
+                nb[e] = pb[e];
+            }
+            if (tvb) {
+#pragma unroll
+                for (int a = 0; a < RX; ++a) {
+                    loX[a] = (enx && xv[a]) ? __ldg(P.x_min + (int64_t)k * NX + l * RX + a) : loX[a];
+                    hiX[a] = (enx && xv[a]) ? __ldg(P.x_max + (int64_t)k * NX + l * RX + a) : hiX[a];
+                }
+                if (HASU) {
+#pragma unroll
+                    for (int b = 0; b < RU; ++b) {
+                        loU[b] = (enu && uv[b]) ? __ldg(P.u_min + (int64_t)k * NU + l * RU + b) : loU[b];
+                        hiU[b] = (enu && uv[b]) ? __ldg(P.u_max + (int64_t)k * NU + l * RU + b) : hiU[b];
+                    }
+                }
+            }
+#pragma unroll
+            for (int a = 0; a < RX; ++a) {  // vnew = clamp(x + g), g += x - vnew
+                T vo = pa[a];
+                if constexpr (SLOW) {
+                    if (vin) vo = (P.s_v && xv[a]) ? P.s_v[offx + (int64_t)k * NX + l * RX + a] : T(0);
+                }
+                const T v = clamp_box<FAST>(xo[a] + pb[a], loX[a], hiX[a]);
+                na[a] = v;
+                nb[a] = (pb[a] + xo[a]) - v;
+                if constexpr (SLOW) {
+                    if (busy && xv[a] && P.s_v) P.s_v[offx + (int64_t)k * NX + l * RX + a] = vo;  // work->v of this iteration
+                }
+                rpx = absmax(rpx, xo[a] - v);
+                rdx = absmax(rdx, vo - v);
+            }
+            if (HASU) {
+#pragma unroll
+                for (int b = 0; b < RU; ++b) {
+                    T zo = pa[RX + b];
+                    if constexpr (SLOW) {
+                        if (vin) zo = (P.s_z && uv[b]) ? P.s_z[offu + (int64_t)k * NU + l * RU + b] : T(0);
+                    }
+                    const T z = clamp_box<FAST>(u[b] + pb[RX + b], loU[b], hiU[b]);
+                    na[RX + b] = z;
+                    nb[RX + b] = (pb[RX + b] + u[b]) - z;
+                    if constexpr (SLOW) {
+                        if (busy && uv[b] && P.s_z) P.s_z[offu + (int64_t)k * NU + l * RU + b] = zo;
+                    }
+                    rpu = absmax(rpu, u[b] - z);
+                    rdu = absmax(rdu, zo - z);
+                }
+            }
+            if (busy) {
+                store_pack(aPA, k, na);
+                store_pack(aPB, k, nb);
+            }
+        };
+        for (int k = 0; k < N - 1; ++k) {
+            T u[RU], Uf[NU], t1[RX + RU], bu[RX];
+            dots<FAST>(mS1f, Xf, t1);  // [A x_k ; Kinf x_k]
+#pragma unroll
+            for (int b = 0; b < RU; ++b) {  // u_k = -(Kinf x_k) - d_k
+                const T d = lds(aD + (unsigned)k * DSTR + (unsigned)(b * 32) * ES, T());
+                u[b] = (-t1[RX + b]) - d;
+            }
+            gather_u(u, Uf);
+            column(k, true, u);
+            dots<FAST>(mB, Uf, bu);
+#pragma unroll
+            for (int a = 0; a < RX; ++a) xo[a] = (t1[a] + bu[a]) + vf[a];  // x_{k+1} = (A x_k + B u_k) + f
+            gather_x(xo, Xf);
+        }
         {
-            float4 *w4 = reinterpret_cast<float4 *>(wbase);
-            const int n4 = (int)((size_t)warp_elems * sizeof(T) / 16);
-            for (int w = lane; w < n4; w += 32) w4[w] = make_float4(0.f, 0.f, 0.f, 0.f);
+            T udummy[RU];
+#pragma unroll
+            for (int b = 0; b < RU; ++b) udummy[b] = T(0);
+            column(N - 1, false, udummy);
+        }
+    };
+
+    // ---- cooperative (all 32 lanes) load of instance `ib` into slot `s`: zero the slot's shared-memory state,
+    // read a warm start, and set up the slot's lanes (x0 rows, terminal-cost constant, reference pointers) ----
+    auto load_slot = [&](int s, int64_t ib) {
+        // the slot owns L consecutive lanes of every [k][lane][PVP] row and of every [k][b][lane] row of d
+        for (int e = lane; e < N * L * PVP; e += 32) {
+            const int k = e / (L * PVP), w = e - k * (L * PVP);
+            gPA[(k * 32 + s * L) * PVP + w] = T(0);
+            gPB[(k * 32 + s * L) * PVP + w] = T(0);
+        }
+        for (int e = lane; e < (N - 1) * RU * L; e += 32) {
+            const int kb = e / L, w = e - kb * L;
+            gD[kb * 32 + s * L + w] = T(0);
         }
         __syncwarp();
         if (!cold) {
-            for (int s = 0; s < IPW; ++s) {
-                const int64_t ib = (int64_t)grp * IPW + s;
-                if (ib >= P.B) break;
-                const int64_t ox = ib * (int64_t)N * NX, ou = ib * (int64_t)(N - 1) * NU;
-                for (int e = lane; e < N * NX; e += 32) {
-                    const int k = e / NX, i = e - k * NX;
-                    const int w = idx_x(s, k, i);
-                    gPA[w] = P.s_vnew ? P.s_vnew[ox + e] : T(0);
-                    gPB[w] = P.s_g ? P.s_g[ox + e] : T(0);
-                }
-                for (int e = lane; e < (N - 1) * NU; e += 32) {
-                    const int k = e / NU, j = e - k * NU;
-                    const int w = idx_u(s, k, j);
-                    gPA[w] = P.s_znew ? P.s_znew[ou + e] : T(0);
-                    gPB[w] = P.s_y ? P.s_y[ou + e] : T(0);
-                }
+            const int64_t ox = ib * (int64_t)N * NX, ou = ib * (int64_t)(N - 1) * NU;
+            for (int e = lane; e < N * NX; e += 32) {
+                const int k = e / NX, i = e - k * NX;
+                const int w = idx_x(s, k, i);
+                gPA[w] = P.s_vnew ? P.s_vnew[ox + e] : T(0);
+                gPB[w] = P.s_g ? P.s_g[ox + e] : T(0);
+            }
+            for (int e = lane; e < (N - 1) * NU; e += 32) {
+                const int k = e / NU, j = e - k * NU;
+                const int w = idx_u(s, k, j);
+                gPA[w] = P.s_znew ? P.s_znew[ou + e] : T(0);
+                gPB[w] = P.s_y ? P.s_y[ou + e] : T(0);
             }
             __syncwarp();
         }
-        // x0 (own rows) and the iteration-invariant part of the terminal cost: -(Pinf^T xref_{N-1})
-        T x0o[RX], pterm[RX];
-        {
+        // pull the instance's reference trajectory into L2 now: the backward pass re-reads one column of it per knot
+        // point and iteration, and with one warp per scheduler a DRAM miss there is fully exposed
+        if (P.xref_pi) {
+            const char *xb = reinterpret_cast<const char *>(P.Xref + ib * (int64_t)N * NX);
+            for (int o = lane * 128; o < (int)(N * NX * sizeof(T)); o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(xb + o));
+        }
+        if (has_uref && P.uref_pi) {
+            const char *ub = reinterpret_cast<const char *>(P.Uref + ib * (int64_t)(N - 1) * NU);
+            for (int o = lane * 128; o < (int)((N - 1) * NU * sizeof(T)); o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(ub + o));
+        }
+        if (slot == s) {
+            inst = ib;
+            busy = true;
+            it = 0;
+            solved = 0;
+            res_px = res_dx = res_pu = res_du = T(0);
+            offx = ib * (int64_t)N * NX;
+            offu = ib * (int64_t)(N - 1) * NU;
+            xrefp = P.Xref + (P.xref_pi ? offx : 0) + l * RX;
+            urefp = has_uref ? P.Uref + (P.uref_pi ? offu : 0) + l * RU : P.Xref;
+            // x0 (own rows) and the iteration-invariant part of the terminal cost: -(Pinf^T xref_{N-1})
             T xr[NX];
             const T *xl = xrefp - l * RX + (int64_t)(N - 1) * NX;
 #pragma unroll
@@ -333,246 +464,56 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
 #pragma unroll
             for (int a = 0; a < RX; ++a) {
                 const int i = l * RX + a, ii = xv[a] ? i : 0;
-                x0o[a] = xv[a] ? __ldg(P.x0 + bi * NX + ii) : T(0);
-                T s = xr[0] * __ldg(P.Pinf_g + 0 + NX * ii);
+                x0o[a] = xv[a] ? __ldg(P.x0 + ib * NX + ii) : T(0);
+                T sacc = xr[0] * __ldg(P.Pinf_g + 0 + NX * ii);
 #pragma unroll
-                for (int m = 1; m < NX; ++m) s = mac<FAST>(s, xr[m], __ldg(P.Pinf_g + m + NX * ii));
-                pterm[a] = xv[a] ? -s : T(0);
+                for (int m = 1; m < NX; ++m) sacc = mac<FAST>(sacc, xr[m], __ldg(P.Pinf_g + m + NX * ii));
+                pterm[a] = xv[a] ? -sacc : T(0);
             }
         }
+        __syncwarp();
+    };
 
-        int it_done = 0, solved = 0;
-        bool active = live;
-        T res_px = T(0), res_dx = T(0), res_pu = T(0), res_du = T(0);
-
-        // linear cost of column k for this lane's rows (update_linear_cost, admm.cpp:266-280):
-        //   q = -(xref*Qd) - rho*(vnew - g),  r = -(uref*Rd) - rho*(znew - y)
-        auto cost = [&](int k, const T *xp, const T *up, T (&q)[RX], T (&r)[RU]) {
-            T pa[PVP], pb[PVP];
-            load_pack(aPA, k, pa);
-            load_pack(aPB, k, pb);
-#pragma unroll
-            for (int a = 0; a < RX; ++a) {
-                const T xr = xv[a] ? __ldg(xp + a) : T(0);
-                q[a] = nmac<FAST>(-(xr * vQd[a]), rho, pa[a] - pb[a]);
-            }
-#pragma unroll
-            for (int b = 0; b < RU; ++b) {
-                const T ur = (up && uv[b]) ? __ldg(up + b) : T(0);
-                r[b] = nmac<FAST>(-(ur * vRd[b]), rho, pa[RX + b] - pb[RX + b]);
-            }
-        };
-
-        // forward pass fused with slack / dual update / residuals.  SLOW = first iteration of a warm start
-        // (work->v / work->z come from the caller) or work->v / work->z are being persisted.
-        auto forward = [&](auto tag, const bool vin, T &rpx, T &rdx, T &rpu, T &rdu) {
-            constexpr bool SLOW = decltype(tag)::value;
-            T xo[RX], Xf[NX];
-#pragma unroll
-            for (int a = 0; a < RX; ++a) xo[a] = x0o[a];
-            gather_x(xo, Xf);
-            // one column: slack + dual update of this lane's rows, residual maxima; HASU = the column has inputs
-            auto column = [&](int k, const bool HASU, const T (&u)[RU]) {  // always inlined with a literal HASU
-                T pa[PVP], pb[PVP], na[PVP], nb[PVP];
-                load_pack(aPA, k, pa);
-                load_pack(aPB, k, pb);
-#pragma unroll
-                for (int e = 0; e < PVP; ++e) {
-                    na[e] = pa[e];
-                    nb[e] = pb[e];
-                }
-                if (tvb) {
-#pragma unroll
-                    for (int a = 0; a < RX; ++a) {
-                        loX[a] = (enx && xv[a]) ? __ldg(P.x_min + (int64_t)k * NX + l * RX + a) : loX[a];
-                        hiX[a] = (enx && xv[a]) ? __ldg(P.x_max + (int64_t)k * NX + l * RX + a) : hiX[a];
-                    }
-                    if (HASU) {
-#pragma unroll
-                        for (int b = 0; b < RU; ++b) {
-                            loU[b] = (enu && uv[b]) ? __ldg(P.u_min + (int64_t)k * NU + l * RU + b) : loU[b];
-                            hiU[b] = (enu && uv[b]) ? __ldg(P.u_max + (int64_t)k * NU + l * RU + b) : hiU[b];
-                        }
-                    }
-                }
-#pragma unroll
-                for (int a = 0; a < RX; ++a) {  // vnew = clamp(x + g), g += x - vnew
-                    T vo = pa[a];
-                    if constexpr (SLOW) {
-                        if (vin) vo = (P.s_v && xv[a]) ? P.s_v[offx + (int64_t)k * NX + l * RX + a] : T(0);
-                    }
-                    const T v = clamp_box<FAST>(xo[a] + pb[a], loX[a], hiX[a]);
-                    na[a] = v;
-                    nb[a] = (pb[a] + xo[a]) - v;
-                    if constexpr (SLOW) {
-                        if (active && xv[a] && P.s_v) P.s_v[offx + (int64_t)k * NX + l * RX + a] = vo;  // work->v of this iteration
-                    }
-                    rpx = absmax(rpx, xo[a] - v);
-                    rdx = absmax(rdx, vo - v);
-                }
-                if (HASU) {
-#pragma unroll
-                    for (int b = 0; b < RU; ++b) {
-                        T zo = pa[RX + b];
-                        if constexpr (SLOW) {
-                            if (vin) zo = (P.s_z && uv[b]) ? P.s_z[offu + (int64_t)k * NU + l * RU + b] : T(0);
-                        }
-                        const T z = clamp_box<FAST>(u[b] + pb[RX + b], loU[b], hiU[b]);
-                        na[RX + b] = z;
-                        nb[RX + b] = (pb[RX + b] + u[b]) - z;
-                        if constexpr (SLOW) {
-                            if (active && uv[b] && P.s_z) P.s_z[offu + (int64_t)k * NU + l * RU + b] = zo;
-                        }
-                        rpu = absmax(rpu, u[b] - z);
-                        rdu = absmax(rdu, zo - z);
-                    }
-                }
-                if (active) {
-                    store_pack(aPA, k, na);
-                    store_pack(aPB, k, nb);
-                }
-            };
-            for (int k = 0; k < N - 1; ++k) {
-                T u[RU], Uf[NU], t1[RX + RU], bu[RX];
-                dots<FAST>(mS1f, Xf, t1);  // [A x_k ; Kinf x_k]
-#pragma unroll
-                for (int b = 0; b < RU; ++b) {  // u_k = -(Kinf x_k) - d_k
-                    const T d = lds(aD + (unsigned)k * DSTR + (unsigned)(b * 32) * ES, T());
-                    u[b] = (-t1[RX + b]) - d;
-                }
-                gather_u(u, Uf);
-                column(k, true, u);
-                dots<FAST>(mB, Uf, bu);
-#pragma unroll
-                for (int a = 0; a < RX; ++a) xo[a] = (t1[a] + bu[a]) + vf[a];  // x_{k+1} = (A x_k + B u_k) + f
-                gather_x(xo, Xf);
-            }
-            {
-                T udummy[RU];
-#pragma unroll
-                for (int b = 0; b < RU; ++b) udummy[b] = T(0);
-                column(N - 1, false, udummy);
-            }
-        };
-
-        for (int it = 0; it < P.max_iter; ++it) {
-            if (!__any_sync(0xffffffffu, active)) break;
-
-            // ---- terminal cost + backward pass (update_linear_cost fused, software-pipelined by one column) ----
-            T po[RX], Pf[NX];
-            {
-                T pa[PVP], pb[PVP];
-                load_pack(aPA, N - 1, pa);
-                load_pack(aPB, N - 1, pb);
-#pragma unroll
-                for (int a = 0; a < RX; ++a) po[a] = nmac<FAST>(pterm[a], rho, pa[a] - pb[a]);
-            }
-            gather_x(po, Pf);
-            T q[RX], r[RU], Rf[NU];
-            const T *xp = xrefp + (int64_t)(N - 2) * NX;
-            const T *up = urefp ? urefp + (int64_t)(N - 2) * NU : nullptr;
-            cost(N - 2, xp, up, q, r);
-            gather_u(r, Rf);
-            for (int k = N - 2; k >= 0; --k) {
-                // next column's cost (independent of p): overlaps with the dot-product chains below
-                T qn[RX], rn[RU], Rn[NU];
-                if (k > 0) {
-                    xp -= NX;
-                    if (up) up -= NU;
-                    cost(k - 1, xp, up, qn, rn);
-                    gather_u(rn, Rn);
-                }
-                // d_k = Quu_inv ((B^T p_{k+1} + r_k) + BPf)
-                T s[RU], Sf[NU], acc1[RX + RU], kr[RX], dq[RU];
-                dots<FAST>(mS1b, Pf, acc1);  // [AmBKt p_{k+1} ; B^T p_{k+1}]
-#pragma unroll
-                for (int b = 0; b < RU; ++b) s[b] = (acc1[RX + b] + r[b]) + vBPf[b];
-                gather_u(s, Sf);
-                // p_k = ((q_k + AmBKt p_{k+1}) - Kinf^T r_k) + APf
-                dots<FAST>(mKt, Rf, kr);
-#pragma unroll
-                for (int a = 0; a < RX; ++a) po[a] = ((q[a] + acc1[a]) - kr[a]) + vAPf[a];
-                gather_x(po, Pf);
-                dots<FAST>(mQuu, Sf, dq);
-#pragma unroll
-                for (int b = 0; b < RU; ++b)
-                    if (active && uv[b]) sts(aD + (unsigned)k * DSTR + (unsigned)(b * 32) * ES, dq[b]);
-#pragma unroll
-                for (int a = 0; a < RX; ++a) q[a] = qn[a];
-#pragma unroll
-                for (int b = 0; b < RU; ++b) r[b] = rn[b];
-#pragma unroll
-                for (int j = 0; j < NU; ++j) Rf[j] = Rn[j];
-            }
-            __syncwarp();
-
-            T rpx = T(0), rdx = T(0), rpu = T(0), rdu = T(0);
-            const bool vin = (!cold) && it == 0;
-            if (vin || keep_v) forward(BoolTag<true>{}, vin, rpx, rdx, rpu, rdu);
-            else forward(BoolTag<false>{}, false, rpx, rdx, rpu, rdu);
-            __syncwarp();
-            // ---- termination_condition (admm.cpp:310-328), per instance ----
-            rpx = group_max<T, L>(rpx);
-            rdx = group_max<T, L>(rdx);
-            rpu = group_max<T, L>(rpu);
-            rdu = group_max<T, L>(rdu);
-            if (active) {
-                it_done = it + 1;
-                if (it_done % P.check_termination == 0) {
-                    res_px = rpx;
-                    res_dx = rdx * rho;
-                    res_pu = rpu;
-                    res_du = rdu * rho;
-                    if (res_px < P.pri_tol && res_pu < P.pri_tol && res_dx < P.dua_tol && res_du < P.dua_tol) {
-                        solved = 1;
-                        active = false;
-                    }
-                }
-            }
-        }
-
-        // ---- epilogue ----
-        if (live && l == 0) {
-            if (P.iter) P.iter[inst] = it_done;
-            if (P.solved) P.solved[inst] = solved;
+    // ---- cooperative write-back of slot `s` (instance `ib`): solution, info, optional state and rollout ----
+    auto store_slot = [&](int s, int64_t ib) {
+        const int s_solved = __shfl_sync(0xffffffffu, solved, s * L);
+        const int s_it = __shfl_sync(0xffffffffu, it, s * L);
+        if (slot == s && l == 0) {
+            if (P.iter) P.iter[ib] = it;
+            if (P.solved) P.solved[ib] = solved;
             if (P.residuals) {
-                T *r = P.residuals + 4 * inst;
+                T *r = P.residuals + 4 * ib;
                 r[0] = res_px; r[1] = res_dx; r[2] = res_pu; r[3] = res_du;
             }
         }
         __syncwarp();
-        // solution->x = vnew, solution->u = znew; work->vnew/znew/g/y; coalesced transposing copy per instance
-        for (int s = 0; s < IPW; ++s) {
-            const int64_t ib = (int64_t)grp * IPW + s;
-            if (ib >= P.B) break;
-            const int64_t ox = ib * (int64_t)N * NX, ou = ib * (int64_t)(N - 1) * NU;
-            const int s_solved = __shfl_sync(0xffffffffu, solved, s * L);
-            const int s_it = __shfl_sync(0xffffffffu, it_done, s * L);
-            for (int e = lane; e < N * NX; e += 32) {
-                const int k = e / NX, i = e - k * NX;
-                const int w = idx_x(s, k, i);
-                const T v = gPA[w];
-                P.sol_x[ox + e] = v;
-                if (P.s_vnew) P.s_vnew[ox + e] = v;
-                if (P.s_g) P.s_g[ox + e] = gPB[w];
-                // work->v: previous vnew if the solve converged (streamed out during the last forward pass),
-                // else = vnew (admm.cpp:445); untouched when no iteration ran on a warm start
-                if (P.s_v && !s_solved && s_it > 0) P.s_v[ox + e] = v;
-                else if (P.s_v && cold && s_it == 0) P.s_v[ox + e] = T(0);
-            }
-            for (int e = lane; e < (N - 1) * NU; e += 32) {
-                const int k = e / NU, j = e - k * NU;
-                const int w = idx_u(s, k, j);
-                const T z = gPA[w];
-                P.sol_u[ou + e] = z;
-                if (P.s_znew) P.s_znew[ou + e] = z;
-                if (P.s_y) P.s_y[ou + e] = gPB[w];
-                if (P.s_z && !s_solved && s_it > 0) P.s_z[ou + e] = z;
-                else if (P.s_z && cold && s_it == 0) P.s_z[ou + e] = T(0);
-            }
+        const int64_t ox = ib * (int64_t)N * NX, ou = ib * (int64_t)(N - 1) * NU;
+        // solution->x = vnew, solution->u = znew; work->vnew/znew/g/y; coalesced transposing copy
+        for (int e = lane; e < N * NX; e += 32) {
+            const int k = e / NX, i = e - k * NX;
+            const int w = idx_x(s, k, i);
+            const T v = gPA[w];
+            P.sol_x[ox + e] = v;
+            if (P.s_vnew) P.s_vnew[ox + e] = v;
+            if (P.s_g) P.s_g[ox + e] = gPB[w];
+            // work->v: previous vnew if the solve converged (streamed out during the last forward pass),
+            // else = vnew (admm.cpp:445); untouched when no iteration ran on a warm start
+            if (P.s_v && !s_solved && s_it > 0) P.s_v[ox + e] = v;
+            else if (P.s_v && cold && s_it == 0) P.s_v[ox + e] = T(0);
         }
-        // work->x / work->u: replay the last rollout from d and x0 (bit-identical to the last forward pass),
-        // staging it in the (now dead) primal pack so that the write-back is coalesced too
+        for (int e = lane; e < (N - 1) * NU; e += 32) {
+            const int k = e / NU, j = e - k * NU;
+            const int w = idx_u(s, k, j);
+            const T z = gPA[w];
+            P.sol_u[ou + e] = z;
+            if (P.s_znew) P.s_znew[ou + e] = z;
+            if (P.s_y) P.s_y[ou + e] = gPB[w];
+            if (P.s_z && !s_solved && s_it > 0) P.s_z[ou + e] = z;
+            else if (P.s_z && cold && s_it == 0) P.s_z[ou + e] = T(0);
+        }
+        // work->x / work->u: replay the last rollout from d and x0 (bit-identical to the last forward pass), staging it
+        // in this slot's (now dead) primal pack so that the write-back is coalesced too.  Every lane executes the
+        // arithmetic (the gathers are warp-wide); only the lanes of slot s store.
         if (P.s_x || P.s_u) {
             __syncwarp();
             T xo[RX], Xf[NX];
@@ -599,30 +540,124 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
 #pragma unroll
                     for (int a = 0; a < RX; ++a) xo[a] = (t1[a] + bu[a]) + vf[a];
                 }
-                store_pack(aPA, k, na);
+                if (slot == s) store_pack(aPA, k, na);
                 if (k < N - 1) gather_x(xo, Xf);
             }
             __syncwarp();
-            for (int s = 0; s < IPW; ++s) {
-                const int64_t ib = (int64_t)grp * IPW + s;
-                if (ib >= P.B) break;
-                const int64_t ox = ib * (int64_t)N * NX, ou = ib * (int64_t)(N - 1) * NU;
-                const int s_it = __shfl_sync(0xffffffffu, it_done, s * L);
-                if (P.s_x)
-                    for (int e = lane; e < N * NX; e += 32) {
-                        const int k = e / NX, i = e - k * NX;
-                        if (s_it > 0 || k == 0) P.s_x[ox + e] = gPA[idx_x(s, k, i)];
-                        else if (cold) P.s_x[ox + e] = T(0);
-                    }
-                if (P.s_u)
-                    for (int e = lane; e < (N - 1) * NU; e += 32) {
-                        const int k = e / NU, j = e - k * NU;
-                        if (s_it > 0) P.s_u[ou + e] = gPA[idx_u(s, k, j)];
-                        else if (cold) P.s_u[ou + e] = T(0);
-                    }
-            }
+            if (P.s_x)
+                for (int e = lane; e < N * NX; e += 32) {
+                    const int k = e / NX, i = e - k * NX;
+                    if (s_it > 0 || k == 0) P.s_x[ox + e] = gPA[idx_x(s, k, i)];
+                    else if (cold) P.s_x[ox + e] = T(0);
+                }
+            if (P.s_u)
+                for (int e = lane; e < (N - 1) * NU; e += 32) {
+                    const int k = e / NU, j = e - k * NU;
+                    if (s_it > 0) P.s_u[ou + e] = gPA[idx_u(s, k, j)];
+                    else if (cold) P.s_u[ou + e] = T(0);
+                }
         }
         __syncwarp();
+    };
+
+    // ---- persistent loop: every slot runs its own instance; a slot that terminates (converged or max_iter) is
+    // written back and refilled from the global queue immediately, so no lane group waits for the slowest
+    // instance of its warp (termination is per instance, admm.cpp:310-328) ----
+    for (;;) {
+        // 1. retire finished slots / fill empty ones
+        const bool fin = busy && (solved || it >= P.max_iter);
+        const unsigned todo = __ballot_sync(0xffffffffu, (fin || (!busy && want)) && l == 0);
+        for (unsigned m = todo; m; m &= m - 1) {
+            const int s = (__ffs(m) - 1) / L;
+            const int64_t ib_old = __shfl_sync(0xffffffffu, inst, s * L);
+            const int was_busy = __shfl_sync(0xffffffffu, (int)busy, s * L);
+            if (was_busy) store_slot(s, ib_old);
+            unsigned long long nxt = 0;
+            if (lane == 0) nxt = atomicAdd(queue, 1ULL);
+            nxt = __shfl_sync(0xffffffffu, nxt, 0);
+            if ((int64_t)nxt < P.B) {
+                load_slot(s, (int64_t)nxt);
+            } else if (slot == s) {
+                busy = false;
+                want = false;
+            }
+        }
+        if (!__any_sync(0xffffffffu, busy)) break;
+        __syncwarp();
+
+        // 2. ADMM iterations for every busy slot until some slot terminates.  This inner loop has warp-uniform
+        // control flow only, so the compiler keeps the warp converged (no divergence bookkeeping around the
+        // shared-memory gathers).
+        do {
+        // ---- terminal cost + backward pass (update_linear_cost fused, software-pipelined by one column) ----
+        T po[RX], Pf[NX];
+        {
+            T pa[PVP], pb[PVP];
+            load_pack(aPA, N - 1, pa);
+            load_pack(aPB, N - 1, pb);
+#pragma unroll
+            for (int a = 0; a < RX; ++a) po[a] = nmac<FAST>(pterm[a], rho, pa[a] - pb[a]);
+        }
+        gather_x(po, Pf);
+        T q[RX], r[RU], Rf[NU];
+        const T *xp = xrefp + (int64_t)(N - 2) * NX;
+        const T *up = urefp + (has_uref ? (int64_t)(N - 2) * NU : 0);
+        cost(N - 2, xp, up, q, r);
+        gather_u(r, Rf);
+        for (int k = N - 2; k >= 0; --k) {
+            // next column's cost (independent of p): overlaps with the dot-product chains below
+            T qn[RX], rn[RU], Rn[NU];
+            if (k > 0) {
+                xp -= NX;
+                if (has_uref) up -= NU;
+                cost(k - 1, xp, up, qn, rn);
+                gather_u(rn, Rn);
+            }
+            // d_k = Quu_inv ((B^T p_{k+1} + r_k) + BPf)
+            T s_[RU], Sf[NU], acc1[RX + RU], kr[RX], dq[RU];
+            dots<FAST>(mS1b, Pf, acc1);  // [AmBKt p_{k+1} ; B^T p_{k+1}]
+#pragma unroll
+            for (int b = 0; b < RU; ++b) s_[b] = (acc1[RX + b] + r[b]) + vBPf[b];
+            gather_u(s_, Sf);
+            // p_k = ((q_k + AmBKt p_{k+1}) - Kinf^T r_k) + APf
+            dots<FAST>(mKt, Rf, kr);
+#pragma unroll
+            for (int a = 0; a < RX; ++a) po[a] = ((q[a] + acc1[a]) - kr[a]) + vAPf[a];
+            gather_x(po, Pf);
+            dots<FAST>(mQuu, Sf, dq);
+#pragma unroll
+            for (int b = 0; b < RU; ++b)
+                if (busy && uv[b]) sts(aD + (unsigned)k * DSTR + (unsigned)(b * 32) * ES, dq[b]);
+#pragma unroll
+            for (int a = 0; a < RX; ++a) q[a] = qn[a];
+#pragma unroll
+            for (int b = 0; b < RU; ++b) r[b] = rn[b];
+#pragma unroll
+            for (int j = 0; j < NU; ++j) Rf[j] = Rn[j];
+        }
+        __syncwarp();
+
+        T rpx = T(0), rdx = T(0), rpu = T(0), rdu = T(0);
+        const bool vin = busy && (!cold) && it == 0;  // work->v / work->z come from the caller on the first iteration
+        if (keep_v || __any_sync(0xffffffffu, vin)) forward(BoolTag<true>{}, vin, rpx, rdx, rpu, rdu);
+        else forward(BoolTag<false>{}, false, rpx, rdx, rpu, rdu);
+        __syncwarp();
+        // ---- termination_condition (admm.cpp:310-328), per instance ----
+        rpx = group_max<T, L>(rpx);
+        rdx = group_max<T, L>(rdx);
+        rpu = group_max<T, L>(rpu);
+        rdu = group_max<T, L>(rdu);
+        if (busy) {
+            it += 1;
+            if (it % P.check_termination == 0) {
+                res_px = rpx;
+                res_dx = rdx * rho;
+                res_pu = rpu;
+                res_du = rdu * rho;
+                if (res_px < P.pri_tol && res_pu < P.pri_tol && res_dx < P.dua_tol && res_du < P.dua_tol) solved = 1;
+            }
+        }
+        } while (!__any_sync(0xffffffffu, busy && (solved || it >= P.max_iter)));
     }
 }
 

@@ -298,20 +298,22 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
 
     // linear cost of column k for this lane's rows (update_linear_cost, admm.cpp:266-280):
     //   q = -(xref*Qd) - rho*(vnew - g),  r = -(uref*Rd) - rho*(znew - y)
-    auto cost = [&](int k, const T *xp, const T *up, T (&q)[RX], T (&r)[RU]) {
-        T pa[PVP], pb[PVP];
+    // split in two so that the global (reference) and shared (state) loads of column k-1 are issued at the top of
+    // backward step k and consumed only at its end, behind the dot-product chains: with one warp per scheduler a
+    // load consumed right after issue is fully exposed (per-instance references come from L2/HBM)
+    auto cost_load = [&](int k, const T *xp, const T *up, T (&xr)[RX], T (&ur)[RU], T (&pa)[PVP], T (&pb)[PVP]) {
+#pragma unroll
+        for (int a = 0; a < RX; ++a) xr[a] = xv[a] ? __ldg(xp + a) : T(0);
+#pragma unroll
+        for (int b = 0; b < RU; ++b) ur[b] = (has_uref && uv[b]) ? __ldg(up + b) : T(0);
         load_pack(aPA, k, pa);
         load_pack(aPB, k, pb);
+    };
+    auto cost_eval = [&](const T (&xr)[RX], const T (&ur)[RU], const T (&pa)[PVP], const T (&pb)[PVP], T (&q)[RX], T (&r)[RU]) {
 #pragma unroll
-        for (int a = 0; a < RX; ++a) {
-            const T xr = xv[a] ? __ldg(xp + a) : T(0);
-            q[a] = nmac<FAST>(-(xr * vQd[a]), rho, pa[a] - pb[a]);
-        }
+        for (int a = 0; a < RX; ++a) q[a] = nmac<FAST>(-(xr[a] * vQd[a]), rho, pa[a] - pb[a]);
 #pragma unroll
-        for (int b = 0; b < RU; ++b) {
-            const T ur = (has_uref && uv[b]) ? __ldg(up + b) : T(0);
-            r[b] = nmac<FAST>(-(ur * vRd[b]), rho, pa[RX + b] - pb[RX + b]);
-        }
+        for (int b = 0; b < RU; ++b) r[b] = nmac<FAST>(-(ur[b] * vRd[b]), rho, pa[RX + b] - pb[RX + b]);
     };
 
     // forward pass fused with slack / dual update / residuals.  SLOW = some slot is in the first iteration of a
@@ -409,15 +411,18 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
     // ---- cooperative (all 32 lanes) load of instance `ib` into slot `s`: zero the slot's shared-memory state,
     // read a warm start, and set up the slot's lanes (x0 rows, terminal-cost constant, reference pointers) ----
     auto load_slot = [&](int s, int64_t ib) {
-        // the slot owns L consecutive lanes of every [k][lane][PVP] row and of every [k][b][lane] row of d
-        for (int e = lane; e < N * L * PVP; e += 32) {
-            const int k = e / (L * PVP), w = e - k * (L * PVP);
-            gPA[(k * 32 + s * L) * PVP + w] = T(0);
-            gPB[(k * 32 + s * L) * PVP + w] = T(0);
-        }
-        for (int e = lane; e < (N - 1) * RU * L; e += 32) {
-            const int kb = e / L, w = e - kb * L;
-            gD[kb * 32 + s * L + w] = T(0);
+        // the slot owns L consecutive lanes (L*PVP contiguous elements = VPK 16-byte vectors) of every [k][lane][PVP]
+        // row of PA and PB; d is always written before it is read and needs no initialisation
+        {
+            constexpr int VPK = (L * PVP * (int)sizeof(T)) / 16;  // vectors per knot point of one slot
+            float4 *a4 = reinterpret_cast<float4 *>(gPA), *b4 = reinterpret_cast<float4 *>(gPB);
+            constexpr int ROW4 = (32 * PVP * (int)sizeof(T)) / 16;  // vectors per knot point of the whole warp
+            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int e = lane; e < N * VPK; e += 32) {
+                const int k = e / VPK, w = e - k * VPK;
+                a4[k * ROW4 + s * VPK + w] = z4;
+                b4[k * ROW4 + s * VPK + w] = z4;
+            }
         }
         __syncwarp();
         if (!cold) {
@@ -563,6 +568,8 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
     // ---- persistent loop: every slot runs its own instance; a slot that terminates (converged or max_iter) is
     // written back and refilled from the global queue immediately, so no lane group waits for the slowest
     // instance of its warp (termination is per instance, admm.cpp:310-328) ----
+    unsigned long long next_idx = 0;  // one queue ticket is always held in advance (its latency overlaps the refill work)
+    if (lane == 0) next_idx = atomicAdd(queue, 1ULL);
     for (;;) {
         // 1. retire finished slots / fill empty ones
         const bool fin = busy && (solved || it >= P.max_iter);
@@ -572,9 +579,8 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
             const int64_t ib_old = __shfl_sync(0xffffffffu, inst, s * L);
             const int was_busy = __shfl_sync(0xffffffffu, (int)busy, s * L);
             if (was_busy) store_slot(s, ib_old);
-            unsigned long long nxt = 0;
-            if (lane == 0) nxt = atomicAdd(queue, 1ULL);
-            nxt = __shfl_sync(0xffffffffu, nxt, 0);
+            const unsigned long long nxt = __shfl_sync(0xffffffffu, next_idx, 0);
+            if (lane == 0 && (int64_t)nxt < P.B) next_idx = atomicAdd(queue, 1ULL);
             if ((int64_t)nxt < P.B) {
                 load_slot(s, (int64_t)nxt);
             } else if (slot == s) {
@@ -602,17 +608,21 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
         T q[RX], r[RU], Rf[NU];
         const T *xp = xrefp + (int64_t)(N - 2) * NX;
         const T *up = urefp + (has_uref ? (int64_t)(N - 2) * NU : 0);
-        cost(N - 2, xp, up, q, r);
+        {
+            T xr[RX], ur[RU], pa[PVP], pb[PVP];
+            cost_load(N - 2, xp, up, xr, ur, pa, pb);
+            cost_eval(xr, ur, pa, pb, q, r);
+        }
         gather_u(r, Rf);
         for (int k = N - 2; k >= 0; --k) {
-            // next column's cost (independent of p): overlaps with the dot-product chains below
-            T qn[RX], rn[RU], Rn[NU];
+            // next column's cost inputs (independent of p): issued now, consumed at the end of this step
+            T xr_n[RX], ur_n[RU], pa_n[PVP], pb_n[PVP];
+            const int kn = (k > 0) ? k - 1 : 0;  // clamped: the k = 0 step re-reads column 0 and discards it
             if (k > 0) {
                 xp -= NX;
                 if (has_uref) up -= NU;
-                cost(k - 1, xp, up, qn, rn);
-                gather_u(rn, Rn);
             }
+            cost_load(kn, xp, up, xr_n, ur_n, pa_n, pb_n);
             // d_k = Quu_inv ((B^T p_{k+1} + r_k) + BPf)
             T s_[RU], Sf[NU], acc1[RX + RU], kr[RX], dq[RU];
             dots<FAST>(mS1b, Pf, acc1);  // [AmBKt p_{k+1} ; B^T p_{k+1}]
@@ -628,12 +638,8 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
 #pragma unroll
             for (int b = 0; b < RU; ++b)
                 if (busy && uv[b]) sts(aD + (unsigned)k * DSTR + (unsigned)(b * 32) * ES, dq[b]);
-#pragma unroll
-            for (int a = 0; a < RX; ++a) q[a] = qn[a];
-#pragma unroll
-            for (int b = 0; b < RU; ++b) r[b] = rn[b];
-#pragma unroll
-            for (int j = 0; j < NU; ++j) Rf[j] = Rn[j];
+            cost_eval(xr_n, ur_n, pa_n, pb_n, q, r);
+            gather_u(r, Rf);
         }
         __syncwarp();
 

@@ -716,6 +716,20 @@ int tinympc_b200_solve_host(tinympc_b200_solver_t *s, const tinympc_batch_t *io)
     int64_t chunk = B;
     if (B > 16384) chunk = std::max<int64_t>(8192, (B + 7) / 8);
     chunk = (chunk + 31) / 32 * 32;
+    {   // the persistent GPI kernel holds sm_count * instances_per_cta instances at a time: make a chunk a whole
+        // number of such waves so that no chunk ends on a mostly empty wave
+        const Features ft = features(s);
+        int smem = 0;
+        const int fam = resolve_family(s, ft, &smem);
+        if (fam == TINYMPC_KERNEL_GPI && s->dim->gpi_instances_per_cta && B > 16384) {
+            const int64_t wave = (int64_t)s->sm_count * s->dim->gpi_instances_per_cta(s->dtype, s->N, s->max_smem_optin);
+            if (wave > 0 && wave < B) chunk = std::max<int64_t>(1, (chunk + wave / 2) / wave) * wave;
+        }
+    }
+    if (const char *e = std::getenv("TINYMPC_HOST_CHUNK")) {  // experiment knob
+        long long v = std::atoll(e);
+        if (v > 0) chunk = std::min<int64_t>(B, (v + 31) / 32 * 32);
+    }
     const int64_t nchunks = (B + chunk - 1) / chunk;
     const size_t align = 256;
     auto padded = [&](size_t n) { return (n + align - 1) / align * align; };

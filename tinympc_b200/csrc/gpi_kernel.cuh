@@ -568,8 +568,6 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
     // ---- persistent loop: every slot runs its own instance; a slot that terminates (converged or max_iter) is
     // written back and refilled from the global queue immediately, so no lane group waits for the slowest
     // instance of its warp (termination is per instance, admm.cpp:310-328) ----
-    unsigned long long next_idx = 0;  // one queue ticket is always held in advance (its latency overlaps the refill work)
-    if (lane == 0) next_idx = atomicAdd(queue, 1ULL);
     for (;;) {
         // 1. retire finished slots / fill empty ones
         const bool fin = busy && (solved || it >= P.max_iter);
@@ -578,9 +576,13 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
             const int s = (__ffs(m) - 1) / L;
             const int64_t ib_old = __shfl_sync(0xffffffffu, inst, s * L);
             const int was_busy = __shfl_sync(0xffffffffu, (int)busy, s * L);
+            // the queue ticket is requested before the write-back of the finished instance so that the atomic's
+            // latency hides behind it.  (Never hold a ticket in advance: measured on B200, a ticket prefetched by every
+            // warp kept up to 592 instances hostage until a slot freed up and cost a whole extra wave per launch.)
+            unsigned long long nxt = 0;
+            if (lane == 0) nxt = atomicAdd(queue, 1ULL);
             if (was_busy) store_slot(s, ib_old);
-            const unsigned long long nxt = __shfl_sync(0xffffffffu, next_idx, 0);
-            if (lane == 0 && (int64_t)nxt < P.B) next_idx = atomicAdd(queue, 1ULL);
+            nxt = __shfl_sync(0xffffffffu, nxt, 0);
             if ((int64_t)nxt < P.B) {
                 load_slot(s, (int64_t)nxt);
             } else if (slot == s) {

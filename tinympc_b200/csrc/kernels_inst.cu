@@ -148,12 +148,27 @@ int gpi_fit(int dtype, int N, int max_smem_optin) {
     return 0;
 }
 
+int gpi_ipc(int dtype, int N, int max_smem_optin) {
+#ifdef TM_WITH_GPI
+    if (dtype == TINYMPC_F32) {
+        const GpiPlan p = gpi_plan<float, TM_NX, TM_NU>(N, max_smem_optin - 64);
+        return p.L ? p.warps * (32 / p.L) : 0;
+    }
+    if (dtype == TINYMPC_F64) {
+        const GpiPlan p = gpi_plan<double, TM_NX, TM_NU>(N, max_smem_optin - 64);
+        return p.L ? p.warps * (32 / p.L) : 0;
+    }
+#endif
+    (void)dtype; (void)N; (void)max_smem_optin;
+    return 0;
+}
+
 }  // namespace
 }  // namespace tmpc
 
 #define TM_CAT2(a, b, c) a##b##_##c
 #define TM_CAT(a, b, c) TM_CAT2(a, b, c)
 extern "C" const tmpc::DimEntry *TM_CAT(tm_dim_entry_, TM_NX, TM_NU)() {
-    static const tmpc::DimEntry e = {TM_NX, TM_NU, &tmpc::launch, &tmpc::gpi_fit};
+    static const tmpc::DimEntry e = {TM_NX, TM_NU, &tmpc::launch, &tmpc::gpi_fit, &tmpc::gpi_ipc};
     return &e;
 }

@@ -320,3 +320,24 @@ def test_time_varying_bounds(kernel):
     o = _port(prob, st, inst["x0"], inst["Xref"], None, None, True, want)
     for key in H.OUT_KEYS + H.BOX_STATE:
         assert H.bits_equal(g[key], o[key]), key
+
+
+@pytest.mark.parametrize("kernel", ["tpi", "gpi"])
+def test_max_iter_zero_returns_the_warm_state(kernel):
+    """max_iter = 0: solve() skips its loop (admm.cpp:378) and reports solution = vnew/znew as they stand, iter = 0."""
+    spec = wl.quadrotor(N=10)
+    dt = np.float32
+    prob = setup_problem(spec, dt)
+    st = abi.Settings.from_buffer_copy(spec.settings)
+    inst = wl.tracking_instances(40, N=10, seed=2, dtype=dt)
+    solver = _mk_solver(prob, spec.settings, kernel)
+    first = solver.solve(inst["x0"], inst["Xref"], None, cold_start=True, want_state=tuple(H.BOX_STATE))
+    st.max_iter = 0
+    solver0 = _mk_solver(prob, st, kernel)
+    state_g = {n: first[n].copy() for n in H.BOX_STATE}
+    state_o = {n: first[n].copy() for n in H.BOX_STATE}
+    g = solver0.solve(inst["x0"], inst["Xref"], None, state=state_g, cold_start=False)
+    o = _port(prob, st, inst["x0"], inst["Xref"], None, state_o, False, ())
+    for key in H.OUT_KEYS + H.BOX_STATE:
+        assert H.bits_equal(g[key], o[key]), key
+    assert (g["iter"] == 0).all() and H.bits_equal(g["sol_x"], first["vnew"])

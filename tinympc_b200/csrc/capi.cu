@@ -179,7 +179,7 @@ int check_ready(const tinympc_b200_solver *s) {
     return 0;
 }
 
-int resolve_family(const tinympc_b200_solver *s, const Features &ft, int *smem_out) {
+int resolve_family(const tinympc_b200_solver *s, const Features &ft, int *smem_out, int64_t B = 0) {
     int smem = 0;
     bool gpi_ok = false;
     if (!ft.ext && s->dim->gpi_fit) {
@@ -190,7 +190,13 @@ int resolve_family(const tinympc_b200_solver *s, const Features &ft, int *smem_o
     if (s->family == TINYMPC_KERNEL_GPI) return gpi_ok ? TINYMPC_KERNEL_GPI : -1;
     if (s->family == TINYMPC_KERNEL_TPI) return TINYMPC_KERNEL_TPI;
     if (s->family == TINYMPC_KERNEL_HYBRID) return gpi_ok ? TINYMPC_KERNEL_HYBRID : -1;
-    return gpi_ok ? TINYMPC_KERNEL_GPI : TINYMPC_KERNEL_TPI;  // AUTO (HYBRID stays opt-in: profiles/README.md)
+    if (!gpi_ok) return TINYMPC_KERNEL_TPI;
+    // AUTO: GPI unless shared memory leaves it fewer than one warp per scheduler (long horizons / wide states) AND the
+    // batch is large enough to fill the GPU with one thread per instance (profiles/r01_sweep_1gpu.md).  HYBRID is opt-in.
+    const int plan = s->dim->gpi_instances_per_cta ? s->dim->gpi_instances_per_cta(s->dtype, s->N, s->max_smem_optin) : 0;
+    const int warps = plan >> 16;
+    if (warps > 0 && warps < 4 && B >= (int64_t)s->sm_count * 384) return TINYMPC_KERNEL_TPI;
+    return TINYMPC_KERNEL_GPI;
 }
 
 // Fraction of a batch the GPI kernel takes in HYBRID mode.  GPI (shared-memory bound: one CTA per SM, 4 warps,
@@ -311,7 +317,7 @@ int enqueue(tinympc_b200_solver *s, const tinympc_batch_t *io, cudaStream_t stre
     if (io->B <= 0) return TINYMPC_OK;
     const Features ft = features(s);
     int smem = 0;
-    const int family = resolve_family(s, ft, &smem);
+    const int family = resolve_family(s, ft, &smem, io->B);
     if (family < 0) return fail(TINYMPC_ERR_UNSUPPORTED, "GPI kernel requested but it does not support this problem (features or shared-memory footprint)");
     int64_t launches = 0, ctas = 0;
     tmpc::LaunchDesc d;
@@ -720,9 +726,9 @@ int tinympc_b200_solve_host(tinympc_b200_solver_t *s, const tinympc_batch_t *io)
         // number of such waves so that no chunk ends on a mostly empty wave
         const Features ft = features(s);
         int smem = 0;
-        const int fam = resolve_family(s, ft, &smem);
+        const int fam = resolve_family(s, ft, &smem, chunk);
         if (fam == TINYMPC_KERNEL_GPI && s->dim->gpi_instances_per_cta && B > 16384) {
-            const int64_t wave = (int64_t)s->sm_count * s->dim->gpi_instances_per_cta(s->dtype, s->N, s->max_smem_optin);
+            const int64_t wave = (int64_t)s->sm_count * (s->dim->gpi_instances_per_cta(s->dtype, s->N, s->max_smem_optin) & 0xffff);
             if (wave > 0 && wave < B) chunk = std::max<int64_t>(1, (chunk + wave / 2) / wave) * wave;
         }
     }

@@ -591,6 +591,7 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
             }
         }
         if (!__any_sync(0xffffffffu, busy)) break;
+        if (__any_sync(0xffffffffu, busy && it >= P.max_iter)) continue;  // max_iter <= 0: retire without iterating
         __syncwarp();
 
         // 2. ADMM iterations for every busy slot until some slot terminates.  This inner loop has warp-uniform

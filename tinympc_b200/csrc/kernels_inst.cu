@@ -152,11 +152,11 @@ int gpi_ipc(int dtype, int N, int max_smem_optin) {
 #ifdef TM_WITH_GPI
     if (dtype == TINYMPC_F32) {
         const GpiPlan p = gpi_plan<float, TM_NX, TM_NU>(N, max_smem_optin - 64);
-        return p.L ? p.warps * (32 / p.L) : 0;
+        return p.L ? ((p.warps << 16) | (p.warps * (32 / p.L))) : 0;
     }
     if (dtype == TINYMPC_F64) {
         const GpiPlan p = gpi_plan<double, TM_NX, TM_NU>(N, max_smem_optin - 64);
-        return p.L ? p.warps * (32 / p.L) : 0;
+        return p.L ? ((p.warps << 16) | (p.warps * (32 / p.L))) : 0;
     }
 #endif
     (void)dtype; (void)N; (void)max_smem_optin;

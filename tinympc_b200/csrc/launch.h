@@ -53,7 +53,7 @@ struct DimEntry {
     launch_fn launch;
     // GPI capability query: shared-memory bytes per CTA for a given (dtype, N) or 0 if GPI not available
     int (*gpi_fit)(int dtype, int N, int max_smem_optin);
-    // instances resident per CTA of the GPI kernel (warps * 32 / lanes_per_instance), 0 if GPI not available
+    // GPI plan for (dtype, N): (warps per CTA << 16) | instances resident per CTA; 0 if GPI is not available
     int (*gpi_instances_per_cta)(int dtype, int N, int max_smem_optin);
 };
 

@@ -157,11 +157,12 @@ typedef struct tinympc_batch {
     int32_t cold_start; /* 1: ignore the contents of `state` on input (all zeros)                 */
     tinympc_state_t state;
 
-    void *sol_x;  /* [B][N][nx]    solution->x = vnew   (admm.cpp:436,452)  required */
-    void *sol_u;  /* [B][N-1][nu]  solution->u = znew   (admm.cpp:437,453)  required */
+    void *sol_x;  /* [B][N][nx]    solution->x = vnew   (admm.cpp:436,452)  may be NULL (e.g. when state.vnew is given) */
+    void *sol_u;  /* [B][N-1][nu]  solution->u = znew   (admm.cpp:437,453)  may be NULL */
     int32_t *iter;   /* [B] solution->iter                                           */
     int32_t *solved; /* [B] solution->solved (tiny_solve returns !solved)            */
     void *residuals; /* [B][4]: primal_state, dual_state, primal_input, dual_input (types.hpp:202-205); may be NULL */
+    void *u0;        /* [B][nu] optional: work->u.col(0), the control every example applies (e.g. quadrotor_hovering.cpp:92) */
 } tinympc_batch_t;
 
 typedef struct tinympc_b200_solver tinympc_b200_solver_t;
@@ -225,10 +226,12 @@ int tinympc_b200_get_stats(const tinympc_b200_solver_t *s, tinympc_b200_stats_t 
 /*
  * Closed-loop helper (the caller of the hot path, e.g. examples/quadrotor_tracking.cpp:105):
  *     x0[b] <- (Adyn * x0[b] + Bdyn * u[b][:,0]) + fdyn        for b in [0, B)
- * with x0 [B][nx] (in/out) and u = work->u [B][N-1][nu], all DEVICE pointers; ascending-k sums, no FMA.
- * Lets thousands of simulated plants step without a host round trip between two tinympc_b200_solve calls.
+ * with x0 [B][nx] (in/out) and u pointing at the first control of instance 0, consecutive instances `u_stride`
+ * elements apart (nu for a tinympc_batch_t.u0 buffer, (N-1)*nu for a work->u buffer); DEVICE pointers;
+ * ascending-k sums, no FMA.  Lets thousands of simulated plants step without a host round trip between two
+ * tinympc_b200_solve calls.
  */
-int tinympc_b200_advance(tinympc_b200_solver_t *s, int64_t B, void *x0, const void *u, void *cuda_stream);
+int tinympc_b200_advance(tinympc_b200_solver_t *s, int64_t B, void *x0, const void *u, int64_t u_stride, void *cuda_stream);
 
 /* 1 if a kernel is compiled for (dtype,nx,nu); used by callers to fail early */
 int tinympc_b200_supported(int32_t dtype, int32_t nx, int32_t nu);

@@ -257,8 +257,9 @@ def test_device_resident_closed_loop_matches_oracle(kernel):
             state["g"] = np.zeros_like(state["g"])
             state["y"] = np.zeros_like(state["y"])
         o = _port(prob, st, x0, Xref, None, state, state is None, tuple(H.BOX_STATE))
-        for key in H.OUT_KEYS + H.BOX_STATE:
+        for key in H.OUT_KEYS + list(loop.fields):
             assert H.bits_equal(out[key].cpu().numpy(), o[key]), (k, key)
+        assert H.bits_equal(out["u0"].cpu().numpy(), np.ascontiguousarray(o["u"][:, 0, :])), (k, "u0")
         state = {n: o[n] for n in H.BOX_STATE}
         u0 = o["u"][:, 0, :]
         nxt = np.zeros_like(x0)

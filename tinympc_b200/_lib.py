@@ -46,7 +46,7 @@ def load():
     lib.tinympc_b200_solve.argtypes = [vp, C.POINTER(abi.Batch), vp]
     lib.tinympc_b200_solve_host.argtypes = [vp, C.POINTER(abi.Batch)]
     lib.tinympc_b200_get_stats.argtypes = [vp, C.POINTER(abi.Stats)]
-    lib.tinympc_b200_advance.argtypes = [vp, C.c_int64, vp, vp, vp]
+    lib.tinympc_b200_advance.argtypes = [vp, C.c_int64, vp, vp, C.c_int64, vp]
     lib.tinympc_b200_supported.argtypes = [C.c_int32, C.c_int32, C.c_int32]
     for n in abi.EXPORTS:
         if n not in ("tinympc_b200_last_error", "tinympc_b200_version"):

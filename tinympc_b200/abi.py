@@ -67,6 +67,7 @@ class Batch(C.Structure):
         ("state", State),
         ("sol_x", vp), ("sol_u", vp),
         ("iter", vp), ("solved", vp), ("residuals", vp),
+        ("u0", vp),
     ]
 
 

@@ -23,7 +23,7 @@ namespace {
 
 // x0[b] <- (A x0[b] + B u[b][:,0]) + f ; one thread per (instance, row); matrices column-major in the blob
 template <typename T>
-__global__ void advance_kernel(int nx, int nu, int N, int64_t B, const T *__restrict__ blob, T *x0, const T *__restrict__ u) {
+__global__ void advance_kernel(int nx, int nu, int64_t ustride, int64_t B, const T *__restrict__ blob, T *x0, const T *__restrict__ u) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = t < B * nx;
     T r = T(0);
@@ -31,7 +31,7 @@ __global__ void advance_kernel(int nx, int nu, int N, int64_t B, const T *__rest
         const int64_t b = t / nx;
         const int i = (int)(t - b * nx);
         const T *A = blob, *Bm = blob + nx * nx, *f = Bm + nx * nu;
-        const T *xb = x0 + b * nx, *ub = u + b * (int64_t)(N - 1) * nu;
+        const T *xb = x0 + b * nx, *ub = u + b * ustride;
         T ax = A[i] * xb[0];
         for (int m = 1; m < nx; ++m) ax = ax + A[i + nx * m] * xb[m];
         T bu = Bm[i] * ub[0];
@@ -134,6 +134,7 @@ struct tinympc_b200_solver {
     // workspace
     DevBuf ws;
     DevBuf queue;
+    DevBuf vscratch;
     // host-path staging (per pipeline slot)
     static constexpr int SLOTS = 3;
     DevBuf dio[SLOTS];
@@ -295,6 +296,7 @@ tinympc_batch_t slice_batch(const tinympc_b200_solver *s, const tinympc_batch_t 
     o.iter = (int32_t *)adv(io.iter, sizeof(int32_t));
     o.solved = (int32_t *)adv(io.solved, sizeof(int32_t));
     o.residuals = adv(io.residuals, 4 * es);
+    o.u0 = adv(io.u0, es * s->nu);
     return o;
 }
 
@@ -313,7 +315,7 @@ int64_t tpi_chunk_instances(const tinympc_b200_solver *s, const Features &ft, in
 // enqueue one batched solve on `stream` (device pointers); fills stats
 int enqueue(tinympc_b200_solver *s, const tinympc_batch_t *io, cudaStream_t stream, bool timed) {
     if (int rc = check_ready(s)) return rc;
-    if (!io->x0 || !io->Xref || !io->sol_x || !io->sol_u) return fail(TINYMPC_ERR_ARG, "x0, Xref, sol_x, sol_u are required");
+    if (!io->x0 || !io->Xref) return fail(TINYMPC_ERR_ARG, "x0 and Xref are required");
     if (io->B <= 0) return TINYMPC_OK;
     const Features ft = features(s);
     int smem = 0;
@@ -354,6 +356,17 @@ int enqueue(tinympc_b200_solver *s, const tinympc_batch_t *io, cudaStream_t stre
         if (s->queue.ensure(256)) return fail(TINYMPC_ERR_CUDA, "queue allocation failed");
         CUDA_TRY(cudaMemsetAsync(s->queue.p, 0, 256, sg));
         d.work_queue = s->queue.p;
+        d.gpi_vscratch = nullptr;
+        if (io->state.v || io->state.z) {  // previous-iteration slacks are staged in pack layout, one 16-byte store per knot point
+            const int plan = s->dim->gpi_instances_per_cta(s->dtype, s->N, s->max_smem_optin);
+            const int warps = plan >> 16, ipc = plan & 0xffff;
+            const int L = (warps > 0 && ipc > 0) ? 32 * warps / ipc : 4;
+            const int W = s->dtype == TINYMPC_F64 ? 2 : 4;
+            const int pv = (s->nx + L - 1) / L + (s->nu + L - 1) / L;
+            const size_t pvp = (size_t)(pv + W - 1) / W * W;
+            if (s->vscratch.ensure((size_t)Bg * s->N * L * pvp * esize(s->dtype) + 256)) return fail(TINYMPC_ERR_CUDA, "GPI v-scratch allocation failed");
+            d.gpi_vscratch = s->vscratch.p;
+        }
         d.Bpad = (Bg + 31) / 32 * 32;
         d.io = slice_batch(s, *io, 0, Bg);
         int rc = s->dim->launch(&d);
@@ -538,7 +551,7 @@ int tinympc_b200_destroy(tinympc_b200_solver_t *s) {
     if (!s) return TINYMPC_OK;
     cudaSetDevice(s->device);
     DevBuf *bufs[] = {&s->d_xmin, &s->d_xmax, &s->d_umin, &s->d_umax, &s->d_Alin_x, &s->d_blin_x, &s->d_Alin_u,
-                      &s->d_blin_u, &s->d_tvA_x, &s->d_tvb_x, &s->d_tvA_u, &s->d_tvb_u, &s->ws, &s->queue, &s->d_blob};
+                      &s->d_blin_u, &s->d_tvA_x, &s->d_tvb_x, &s->d_tvA_u, &s->d_tvb_u, &s->ws, &s->queue, &s->d_blob, &s->vscratch};
     for (DevBuf *b : bufs) b->release();
     for (int i = 0; i < tinympc_b200_solver::SLOTS; ++i) {
         s->dio[i].release();
@@ -590,7 +603,7 @@ int tinympc_b200_solve(tinympc_b200_solver_t *s, const tinympc_batch_t *io, void
     return enqueue(s, io, (cudaStream_t)cuda_stream, true);
 }
 
-int tinympc_b200_advance(tinympc_b200_solver_t *s, int64_t B, void *x0, const void *u, void *cuda_stream) {
+int tinympc_b200_advance(tinympc_b200_solver_t *s, int64_t B, void *x0, const void *u, int64_t u_stride, void *cuda_stream) {
     if (!s || !x0 || !u) return fail(TINYMPC_ERR_ARG, "null argument");
     if (B <= 0) return TINYMPC_OK;
     CUDA_TRY(cudaSetDevice(s->device));
@@ -600,9 +613,9 @@ int tinympc_b200_advance(tinympc_b200_solver_t *s, int64_t B, void *x0, const vo
     const unsigned blocks = (unsigned)((total + per - 1) / per);
     cudaStream_t st = (cudaStream_t)cuda_stream;
     if (s->dtype == TINYMPC_F32)
-        advance_kernel<float><<<blocks, per, 0, st>>>(s->nx, s->nu, s->N, B, (const float *)s->d_blob.p, (float *)x0, (const float *)u);
+        advance_kernel<float><<<blocks, per, 0, st>>>(s->nx, s->nu, u_stride, B, (const float *)s->d_blob.p, (float *)x0, (const float *)u);
     else
-        advance_kernel<double><<<blocks, per, 0, st>>>(s->nx, s->nu, s->N, B, (const double *)s->d_blob.p, (double *)x0, (const double *)u);
+        advance_kernel<double><<<blocks, per, 0, st>>>(s->nx, s->nu, u_stride, B, (const double *)s->d_blob.p, (double *)x0, (const double *)u);
     CUDA_TRY(cudaGetLastError());
     return TINYMPC_OK;
 }
@@ -652,7 +665,7 @@ bool is_pinned(const void *p) {
 
 int tinympc_b200_solve_host(tinympc_b200_solver_t *s, const tinympc_batch_t *io) {
     if (!s || !io) return fail(TINYMPC_ERR_ARG, "null argument");
-    if (!io->x0 || !io->Xref || !io->sol_x || !io->sol_u) return fail(TINYMPC_ERR_ARG, "x0, Xref, sol_x, sol_u are required");
+    if (!io->x0 || !io->Xref) return fail(TINYMPC_ERR_ARG, "x0 and Xref are required");
     CUDA_TRY(cudaSetDevice(s->device));
     if (int rc = check_ready(s)) return rc;
     const int64_t B = io->B;
@@ -705,8 +718,9 @@ int tinympc_b200_solve_host(tinympc_b200_solver_t *s, const tinympc_batch_t *io)
             fields.push_back({cold ? nullptr : sp[i], sp[i], is_x ? bx : bu, !cold, true, &dp[i]});
         }
     }
-    fields.push_back({nullptr, io->sol_x, bx, false, true, (void **)&dev.sol_x});
-    fields.push_back({nullptr, io->sol_u, bu, false, true, (void **)&dev.sol_u});
+    if (io->sol_x) fields.push_back({nullptr, io->sol_x, bx, false, true, (void **)&dev.sol_x});
+    if (io->sol_u) fields.push_back({nullptr, io->sol_u, bu, false, true, (void **)&dev.sol_u});
+    if (io->u0) fields.push_back({nullptr, io->u0, es * s->nu, false, true, (void **)&dev.u0});
     if (io->iter) fields.push_back({nullptr, io->iter, sizeof(int32_t), false, true, (void **)&dev.iter});
     if (io->solved) fields.push_back({nullptr, io->solved, sizeof(int32_t), false, true, (void **)&dev.solved});
     if (io->residuals) fields.push_back({nullptr, io->residuals, 4 * es, false, true, (void **)&dev.residuals});

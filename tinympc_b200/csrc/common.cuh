@@ -203,9 +203,11 @@ struct KParams {
     T *s_vcnew, *s_zcnew, *s_gc, *s_yc, *s_vlnew, *s_zlnew, *s_gl, *s_yl;
     T *s_vlnew_tv, *s_zlnew_tv, *s_gl_tv, *s_yl_tv;
     // outputs
-    T *sol_x, *sol_u;
+    T *sol_x, *sol_u;  // may be null
     int32_t *iter, *solved;
     T *residuals;
+    T *u0;  // [B][nu] first rollout input, may be null
+    T *gpi_vscratch;  // GPI: [B][N][L][PVP] copy of the previous primal pack (work->v / work->z) while v,z are persisted
     // TPI workspace (structure-of-arrays, 16-byte vectors, [k][vec][Bpad])
     void *w_v[2], *w_z[2], *w_g, *w_y, *w_d;
     void *w_vc, *w_zc, *w_gc, *w_yc, *w_vl, *w_zl, *w_gl, *w_yl, *w_vlt, *w_zlt, *w_glt, *w_ylt;

@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
         for (int a = 0; a < RX; ++a) xo[a] = x0o[a];
         gather_x(xo, Xf);
         // one column: slack + dual update of this lane's rows, residual maxima; HASU = the column has inputs
-        auto column = [&](int k, const bool HASU, const T (&u)[RU]) {  // always inlined with a literal HASU
+        auto column = [&](int k, const bool HASU, const T (&u)[RU], const T (&vprev)[PVP]) {  // always inlined with a literal HASU
             T pa[PVP], pb[PVP], na[PVP], nb[PVP];
             load_pack(aPA, k, pa);
             load_pack(aPB, k, pb);
@@ -352,14 +352,11 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
             for (int a = 0; a < RX; ++a) {  // vnew = clamp(x + g), g += x - vnew
                 T vo = pa[a];
                 if constexpr (SLOW) {
-                    if (vin) vo = (P.s_v && xv[a]) ? P.s_v[offx + (int64_t)k * NX + l * RX + a] : T(0);
+                    if (vin) vo = vprev[a];
                 }
                 const T v = clamp_box<FAST>(xo[a] + pb[a], loX[a], hiX[a]);
                 na[a] = v;
                 nb[a] = (pb[a] + xo[a]) - v;
-                if constexpr (SLOW) {
-                    if (busy && xv[a] && P.s_v) P.s_v[offx + (int64_t)k * NX + l * RX + a] = vo;  // work->v of this iteration
-                }
                 rpx = absmax(rpx, xo[a] - v);
                 rdx = absmax(rdx, vo - v);
             }
@@ -368,14 +365,11 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
                 for (int b = 0; b < RU; ++b) {
                     T zo = pa[RX + b];
                     if constexpr (SLOW) {
-                        if (vin) zo = (P.s_z && uv[b]) ? P.s_z[offu + (int64_t)k * NU + l * RU + b] : T(0);
+                        if (vin) zo = vprev[RX + b];
                     }
                     const T z = clamp_box<FAST>(u[b] + pb[RX + b], loU[b], hiU[b]);
                     na[RX + b] = z;
                     nb[RX + b] = (pb[RX + b] + u[b]) - z;
-                    if constexpr (SLOW) {
-                        if (busy && uv[b] && P.s_z) P.s_z[offu + (int64_t)k * NU + l * RU + b] = zo;
-                    }
                     rpu = absmax(rpu, u[b] - z);
                     rdu = absmax(rdu, zo - z);
                 }
@@ -383,10 +377,44 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
             if (busy) {
                 store_pack(aPA, k, na);
                 store_pack(aPB, k, nb);
+                if constexpr (SLOW) {
+                    // work->v / work->z of this iteration = the primal pack as it was before this column's update
+                    // (kept in pack layout in global scratch: one 16-byte store; transposed out only if the solve converges)
+                    if (P.gpi_vscratch && !vin) {
+                        T *dst = P.gpi_vscratch + ((inst * N + k) * L + l) * PVP;
+#pragma unroll
+                        for (int c = 0; c < NPV; ++c) {
+                            using V16 = typename Vec16<T>::type;
+                            V16 v16;
+                            T *e16 = reinterpret_cast<T *>(&v16);
+#pragma unroll
+                            for (int e = 0; e < W; ++e) e16[e] = pa[c * W + e];
+                            reinterpret_cast<V16 *>(dst)[c] = v16;
+                        }
+                    }
+                }
+            }
+        };
+        auto load_vprev = [&](int k, T (&vp)[PVP]) {  // caller's work->v / work->z column (first warm iteration only)
+#pragma unroll
+            for (int e = 0; e < PVP; ++e) vp[e] = T(0);
+            if constexpr (SLOW) {
+                if (vin && P.gpi_vscratch) {
+                    const T *src = P.gpi_vscratch + ((inst * N + k) * L + l) * PVP;
+#pragma unroll
+                    for (int c = 0; c < NPV; ++c) {
+                        using V16 = typename Vec16<T>::type;
+                        const V16 v16 = reinterpret_cast<const V16 *>(src)[c];
+                        const T *e16 = reinterpret_cast<const T *>(&v16);
+#pragma unroll
+                        for (int e = 0; e < W; ++e) vp[c * W + e] = e16[e];
+                    }
+                }
             }
         };
         for (int k = 0; k < N - 1; ++k) {
-            T u[RU], Uf[NU], t1[RX + RU], bu[RX];
+            T u[RU], Uf[NU], t1[RX + RU], bu[RX], vprev[PVP];
+            load_vprev(k, vprev);
             dots<FAST>(mS1f, Xf, t1);  // [A x_k ; Kinf x_k]
 #pragma unroll
             for (int b = 0; b < RU; ++b) {  // u_k = -(Kinf x_k) - d_k
@@ -394,17 +422,18 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
                 u[b] = (-t1[RX + b]) - d;
             }
             gather_u(u, Uf);
-            column(k, true, u);
+            column(k, true, u, vprev);
             dots<FAST>(mB, Uf, bu);
 #pragma unroll
             for (int a = 0; a < RX; ++a) xo[a] = (t1[a] + bu[a]) + vf[a];  // x_{k+1} = (A x_k + B u_k) + f
             gather_x(xo, Xf);
         }
         {
-            T udummy[RU];
+            T udummy[RU], vprev[PVP];
 #pragma unroll
             for (int b = 0; b < RU; ++b) udummy[b] = T(0);
-            column(N - 1, false, udummy);
+            load_vprev(N - 1, vprev);
+            column(N - 1, false, udummy, vprev);
         }
     };
 
@@ -426,18 +455,86 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
         }
         __syncwarp();
         if (!cold) {
+            // warm start: the instance's vnew/g/znew/y blocks are contiguous in global memory; loads are batched four
+            // deep before the dependent shared-memory stores (one warp cannot hide a load-use pair per iteration)
             const int64_t ox = ib * (int64_t)N * NX, ou = ib * (int64_t)(N - 1) * NU;
-            for (int e = lane; e < N * NX; e += 32) {
-                const int k = e / NX, i = e - k * NX;
-                const int w = idx_x(s, k, i);
-                gPA[w] = P.s_vnew ? P.s_vnew[ox + e] : T(0);
-                gPB[w] = P.s_g ? P.s_g[ox + e] : T(0);
+            constexpr int UNR = 4;
+            for (int e0 = lane; e0 < N * NX; e0 += 32 * UNR) {
+                T va[UNR], vb[UNR];
+#pragma unroll
+                for (int t = 0; t < UNR; ++t) {
+                    const int e = e0 + 32 * t;
+                    const bool ok = e < N * NX;
+                    va[t] = (ok && P.s_vnew) ? P.s_vnew[ox + e] : T(0);
+                    vb[t] = (ok && P.s_g) ? P.s_g[ox + e] : T(0);
+                }
+#pragma unroll
+                for (int t = 0; t < UNR; ++t) {
+                    const int e = e0 + 32 * t;
+                    if (e < N * NX) {
+                        const int k = e / NX, i = e - k * NX;
+                        const int w = idx_x(s, k, i);
+                        gPA[w] = va[t];
+                        gPB[w] = vb[t];
+                    }
+                }
             }
-            for (int e = lane; e < (N - 1) * NU; e += 32) {
-                const int k = e / NU, j = e - k * NU;
-                const int w = idx_u(s, k, j);
-                gPA[w] = P.s_znew ? P.s_znew[ou + e] : T(0);
-                gPB[w] = P.s_y ? P.s_y[ou + e] : T(0);
+            for (int e0 = lane; e0 < (N - 1) * NU; e0 += 32 * UNR) {
+                T va[UNR], vb[UNR];
+#pragma unroll
+                for (int t = 0; t < UNR; ++t) {
+                    const int e = e0 + 32 * t;
+                    const bool ok = e < (N - 1) * NU;
+                    va[t] = (ok && P.s_znew) ? P.s_znew[ou + e] : T(0);
+                    vb[t] = (ok && P.s_y) ? P.s_y[ou + e] : T(0);
+                }
+#pragma unroll
+                for (int t = 0; t < UNR; ++t) {
+                    const int e = e0 + 32 * t;
+                    if (e < (N - 1) * NU) {
+                        const int k = e / NU, j = e - k * NU;
+                        const int w = idx_u(s, k, j);
+                        gPA[w] = va[t];
+                        gPB[w] = vb[t];
+                    }
+                }
+            }
+            // work->v / work->z of the caller (only read by the first iteration's dual residual): staged into the global
+            // scratch in pack layout, so that the first forward pass fetches them with one 16-byte load per knot point
+            if (P.gpi_vscratch) {
+                T *sc = P.gpi_vscratch + ib * (int64_t)N * L * PVP;
+                for (int e0 = lane; e0 < N * NX; e0 += 32 * UNR) {
+                    T va[UNR];
+#pragma unroll
+                    for (int t = 0; t < UNR; ++t) {
+                        const int e = e0 + 32 * t;
+                        va[t] = (e < N * NX && P.s_v) ? P.s_v[ox + e] : T(0);
+                    }
+#pragma unroll
+                    for (int t = 0; t < UNR; ++t) {
+                        const int e = e0 + 32 * t;
+                        if (e < N * NX) {
+                            const int k = e / NX, i = e - k * NX;
+                            sc[(k * L + i / RX) * PVP + (i % RX)] = va[t];
+                        }
+                    }
+                }
+                for (int e0 = lane; e0 < (N - 1) * NU; e0 += 32 * UNR) {
+                    T va[UNR];
+#pragma unroll
+                    for (int t = 0; t < UNR; ++t) {
+                        const int e = e0 + 32 * t;
+                        va[t] = (e < (N - 1) * NU && P.s_z) ? P.s_z[ou + e] : T(0);
+                    }
+#pragma unroll
+                    for (int t = 0; t < UNR; ++t) {
+                        const int e = e0 + 32 * t;
+                        if (e < (N - 1) * NU) {
+                            const int k = e / NU, j = e - k * NU;
+                            sc[(k * L + j / RU) * PVP + RX + (j % RU)] = va[t];
+                        }
+                    }
+                }
             }
             __syncwarp();
         }
@@ -498,23 +595,43 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
             const int k = e / NX, i = e - k * NX;
             const int w = idx_x(s, k, i);
             const T v = gPA[w];
-            P.sol_x[ox + e] = v;
+            if (P.sol_x) P.sol_x[ox + e] = v;
             if (P.s_vnew) P.s_vnew[ox + e] = v;
             if (P.s_g) P.s_g[ox + e] = gPB[w];
-            // work->v: previous vnew if the solve converged (streamed out during the last forward pass),
-            // else = vnew (admm.cpp:445); untouched when no iteration ran on a warm start
+            // work->v: previous vnew if the solve converged (staged in the scratch during the last forward pass; unchanged
+            // if that was the first iteration of a warm start), else = vnew (admm.cpp:445); untouched when no iteration
+            // ran on a warm start
             if (P.s_v && !s_solved && s_it > 0) P.s_v[ox + e] = v;
+            else if (P.s_v && s_solved && !(s_it == 1 && !cold)) P.s_v[ox + e] = P.gpi_vscratch[((ib * N + k) * L + i / RX) * PVP + (i % RX)];
             else if (P.s_v && cold && s_it == 0) P.s_v[ox + e] = T(0);
         }
         for (int e = lane; e < (N - 1) * NU; e += 32) {
             const int k = e / NU, j = e - k * NU;
             const int w = idx_u(s, k, j);
             const T z = gPA[w];
-            P.sol_u[ou + e] = z;
+            if (P.sol_u) P.sol_u[ou + e] = z;
             if (P.s_znew) P.s_znew[ou + e] = z;
             if (P.s_y) P.s_y[ou + e] = gPB[w];
             if (P.s_z && !s_solved && s_it > 0) P.s_z[ou + e] = z;
+            else if (P.s_z && s_solved && !(s_it == 1 && !cold)) P.s_z[ou + e] = P.gpi_vscratch[((ib * N + k) * L + j / RU) * PVP + RX + (j % RU)];
             else if (P.s_z && cold && s_it == 0) P.s_z[ou + e] = T(0);
+        }
+        // work->u.col(0): one rollout step from d_0 (every lane computes, the lanes of slot s store)
+        if (P.u0) {
+            __syncwarp();
+            T xo0[RX], Xf0[NX], t10[RX + RU];
+#pragma unroll
+            for (int a = 0; a < RX; ++a) xo0[a] = x0o[a];
+            gather_x(xo0, Xf0);
+            dots<FAST>(mS1f, Xf0, t10);
+#pragma unroll
+            for (int b = 0; b < RU; ++b) {
+                const T d = lds(aD + (unsigned)(b * 32) * ES, T());
+                T u0v = (-t10[RX + b]) - d;
+                if (s_it == 0) u0v = (!cold && P.s_u) ? P.s_u[ou + l * RU + b] : T(0);
+                if (slot == s && uv[b]) P.u0[ib * NU + l * RU + b] = u0v;
+            }
+            __syncwarp();
         }
         // work->x / work->u: replay the last rollout from d and x0 (bit-identical to the last forward pass), staging it
         // in this slot's (now dead) primal pack so that the write-back is coalesced too.  Every lane executes the

@@ -82,6 +82,8 @@ void fill_params(KParams<T, TM_NX, TM_NU> &P, const LaunchDesc &d) {
     P.s_vlnew_tv = (T *)s.vlnew_tv; P.s_zlnew_tv = (T *)s.zlnew_tv; P.s_gl_tv = (T *)s.gl_tv; P.s_yl_tv = (T *)s.yl_tv;
     P.sol_x = (T *)io.sol_x; P.sol_u = (T *)io.sol_u;
     P.iter = io.iter; P.solved = io.solved; P.residuals = (T *)io.residuals;
+    P.u0 = (T *)io.u0;
+    P.gpi_vscratch = (T *)d.gpi_vscratch;
     P.w_v[0] = d.w_v[0]; P.w_v[1] = d.w_v[1]; P.w_z[0] = d.w_z[0]; P.w_z[1] = d.w_z[1];
     P.w_g = d.w_g; P.w_y = d.w_y; P.w_d = d.w_d;
     P.w_vc = d.w_vc; P.w_zc = d.w_zc; P.w_gc = d.w_gc; P.w_yc = d.w_yc;

@@ -36,6 +36,7 @@ struct LaunchDesc {
     int bounds_tv;
     const void *h_xlo, *h_xhi, *h_ulo, *h_uhi;  // host copies of column 0 of the bounds (native dtype), may be null
     void *work_queue;  // GPI: device int64 counter (zeroed by the caller)
+    void *gpi_vscratch;  // GPI: scratch for work->v / work->z persistence (allocated by the caller when state.v/z given)
 
     cudaStream_t stream;
     int sm_count;

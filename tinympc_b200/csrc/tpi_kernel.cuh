@@ -510,7 +510,7 @@ __global__ void __launch_bounds__(TPI_THREADS, (sizeof(T) == 4 && !EXT) ? 4 : 2)
     for (int k = 0; k < N; ++k) {
         T a[NX];
         if (ran || !cold) SX::load(P.w_v[vfin], k, S, b, a); else zero(a);
-        store_col<T, NX>(P.sol_x + offx + (int64_t)k * NX, a);
+        if (P.sol_x) store_col<T, NX>(P.sol_x + offx + (int64_t)k * NX, a);
         if (P.s_vnew) store_col<T, NX>(P.s_vnew + offx + (int64_t)k * NX, a);
         if (P.s_v && ran && !conv_first) {
             SX::load(P.w_v[vprev], k, S, b, a);
@@ -535,7 +535,7 @@ __global__ void __launch_bounds__(TPI_THREADS, (sizeof(T) == 4 && !EXT) ? 4 : 2)
     for (int k = 0; k < N - 1; ++k) {
         T a[NU];
         if (ran || !cold) SU::load(P.w_z[vfin], k, S, b, a); else zero(a);
-        store_col<T, NU>(P.sol_u + offu + (int64_t)k * NU, a);
+        if (P.sol_u) store_col<T, NU>(P.sol_u + offu + (int64_t)k * NU, a);
         if (P.s_znew) store_col<T, NU>(P.s_znew + offu + (int64_t)k * NU, a);
         if (P.s_z && ran && !conv_first) {
             SU::load(P.w_z[vprev], k, S, b, a);
@@ -556,6 +556,21 @@ __global__ void __launch_bounds__(TPI_THREADS, (sizeof(T) == 4 && !EXT) ? 4 : 2)
             if (P.tvl_u && P.s_zlnew_tv) { SU::load(P.w_zlt, k, S, b, a); store_col<T, NU>(P.s_zlnew_tv + offu + (int64_t)k * NU, a); }
             if (P.tvl_u && P.s_yl_tv) { SU::load(P.w_ylt, k, S, b, a); store_col<T, NU>(P.s_yl_tv + offu + (int64_t)k * NU, a); }
         }
+    }
+    // work->u.col(0): the control every example applies (quadrotor_hovering.cpp:92) — one rollout step from d_0
+    if (P.u0) {
+        T u[NU];
+        zero(u);
+        if (ran) {
+            T d[NU], kx[NU];
+            SU::load(P.w_d, 0, S, b, d);
+            dots_f<FAST, NU, NX>([&](int j, int m) { return P.Kinf[j + NU * m]; }, x0, kx);
+#pragma unroll
+            for (int j = 0; j < NU; ++j) u[j] = (-kx[j]) - d[j];
+        } else if (!cold && P.s_u) {
+            load_col<T, NU>(P.s_u + offu, u);
+        }
+        store_col<T, NU>(P.u0 + b * NU, u);
     }
     // work->x / work->u (the rollout every example applies, e.g. quadrotor_hovering.cpp:92): recomputed
     // from d and x0 with the same arithmetic as the last forward pass — bit-identical to it.

@@ -114,7 +114,8 @@ class BatchedTinySolver:
         return hb
 
     # ---- device buffers (torch tensors on cuda:<device>) ---------------------------------------------
-    def make_device_batch(self, x0, Xref, Uref=None, state=None, cold_start=True, want_state=(), want_residuals=True):
+    def make_device_batch(self, x0, Xref, Uref=None, state=None, cold_start=True, want_state=(), want_residuals=True,
+                          want_u0=False, want_solution=True):
         """Allocate/adopt torch CUDA tensors and build the device-pointer tinympc_batch_t."""
         import torch
 
@@ -143,8 +144,9 @@ class BatchedTinySolver:
                 st[name] = t(state[name], shape)
             elif name in want_state:
                 st[name] = torch.zeros(shape, dtype=tdt, device=dev)
-        out = dict(sol_x=torch.empty((B, p.N, p.nx), dtype=tdt, device=dev),
-                   sol_u=torch.empty((B, p.N - 1, p.nu), dtype=tdt, device=dev),
+        out = dict(sol_x=torch.empty((B, p.N, p.nx), dtype=tdt, device=dev) if want_solution else None,
+                   sol_u=torch.empty((B, p.N - 1, p.nu), dtype=tdt, device=dev) if want_solution else None,
+                   u0=torch.empty((B, p.nu), dtype=tdt, device=dev) if want_u0 else None,
                    iter=torch.zeros(B, dtype=torch.int32, device=dev),
                    solved=torch.zeros(B, dtype=torch.int32, device=dev),
                    residuals=torch.zeros((B, 4), dtype=tdt, device=dev) if want_residuals else None)
@@ -157,7 +159,9 @@ class BatchedTinySolver:
         b.cold_start = int(bool(cold_start))
         for name, a in st.items():
             setattr(b.state, name, a.data_ptr())
-        b.sol_x, b.sol_u = out["sol_x"].data_ptr(), out["sol_u"].data_ptr()
+        b.sol_x = None if out["sol_x"] is None else out["sol_x"].data_ptr()
+        b.sol_u = None if out["sol_u"] is None else out["sol_u"].data_ptr()
+        b.u0 = None if out["u0"] is None else out["u0"].data_ptr()
         b.iter, b.solved = out["iter"].data_ptr(), out["solved"].data_ptr()
         b.residuals = None if out["residuals"] is None else out["residuals"].data_ptr()
         res = dict(out)

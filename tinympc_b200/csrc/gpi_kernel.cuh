@@ -538,15 +538,31 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
             }
             __syncwarp();
         }
-        // pull the instance's reference trajectory into L2 now: the backward pass re-reads one column of it per knot
-        // point and iteration, and with one warp per scheduler a DRAM miss there is fully exposed
-        if (P.xref_pi) {
-            const char *xb = reinterpret_cast<const char *>(P.Xref + ib * (int64_t)N * NX);
-            for (int o = lane * 128; o < (int)(N * NX * sizeof(T)); o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(xb + o));
-        }
-        if (has_uref && P.uref_pi) {
-            const char *ub = reinterpret_cast<const char *>(P.Uref + ib * (int64_t)(N - 1) * NU);
-            for (int o = lane * 128; o < (int)((N - 1) * NU * sizeof(T)); o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(ub + o));
+        // L2 prefetch, one "generation" of tickets ahead: tickets are handed out in order, so instance ib + PF will be
+        // loaded by some warp shortly; touching its per-instance inputs now turns that warp's latency-exposed loads
+        // (one warp per scheduler cannot hide them) into L2 hits.  The current instance's references are touched too.
+        {
+            constexpr int64_t PF = 1024;
+            auto touch = [&](const T *base, int64_t elems) {
+                const char *pb_ = reinterpret_cast<const char *>(base);
+                for (int64_t o = (int64_t)lane * 128; o < elems * (int64_t)sizeof(T); o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pb_ + o));
+            };
+            const int64_t nxN = (int64_t)N * NX, nuN = (int64_t)(N - 1) * NU;
+            if (P.xref_pi) touch(P.Xref + ib * nxN, nxN);
+            if (has_uref && P.uref_pi) touch(P.Uref + ib * nuN, nuN);
+            const int64_t ip = ib + PF;
+            if (ip < P.B) {
+                if (P.xref_pi) touch(P.Xref + ip * nxN, nxN);
+                if (has_uref && P.uref_pi) touch(P.Uref + ip * nuN, nuN);
+                if (!cold) {
+                    if (P.s_vnew) touch(P.s_vnew + ip * nxN, nxN);
+                    if (P.s_g) touch(P.s_g + ip * nxN, nxN);
+                    if (P.s_znew) touch(P.s_znew + ip * nuN, nuN);
+                    if (P.s_y) touch(P.s_y + ip * nuN, nuN);
+                    if (P.s_v && P.gpi_vscratch) touch(P.s_v + ip * nxN, nxN);
+                    if (P.s_z && P.gpi_vscratch) touch(P.s_z + ip * nuN, nuN);
+                }
+            }
         }
         if (slot == s) {
             inst = ib;

@@ -342,3 +342,20 @@ def test_max_iter_zero_returns_the_warm_state(kernel):
     for key in H.OUT_KEYS + H.BOX_STATE:
         assert H.bits_equal(g[key], o[key]), key
     assert (g["iter"] == 0).all() and H.bits_equal(g["sol_x"], first["vnew"])
+
+
+@pytest.mark.parametrize("kernel", ["tpi", "gpi"])
+@pytest.mark.parametrize("N", [2, 3, 5])
+def test_tiny_horizons(N, kernel):
+    """N = 2 is the smallest horizon the reference can represent (one input column)."""
+    spec = wl.quadrotor(N=N)
+    dt = np.float64
+    prob = setup_problem(spec, dt)
+    st = spec.settings
+    inst = wl.tracking_instances(37, N=N, seed=N, dtype=dt)
+    solver = _mk_solver(prob, st, kernel)
+    want = tuple(H.BOX_STATE)
+    g = solver.solve(inst["x0"], inst["Xref"], None, cold_start=True, want_state=want)
+    o = _port(prob, st, inst["x0"], inst["Xref"], None, None, True, want, nthreads=1)
+    for key in H.OUT_KEYS + H.BOX_STATE:
+        assert H.bits_equal(g[key], o[key]), (N, key)

@@ -816,18 +816,17 @@ inline void gpi_consider(int N, int max_smem, GpiPlan &best) {
     if constexpr (gpi_feasible<T, NX, NU, L>()) {
         using Cfg = GpiCfg<NX, NU, L, (int)sizeof(T)>;
         const size_t per_warp = Cfg::warp_elems(N) * sizeof(T);
-        // the TMA staging area must fit inside the first warp's region
-        const size_t blob = (size_t)(3 * NX * NX + 2 * NX * NU + NU * NU + 4 * NX + 2 * NU) * sizeof(T) + 32;
-        if (per_warp < blob) return;
+        // the TMA staging area aliases the start of the state region: the allocation is at least as large as the blob
+        const size_t blob = ((size_t)(3 * NX * NX + 2 * NX * NU + NU * NU + 4 * NX + 2 * NU) * sizeof(T) + 15) / 16 * 16 + 64;
         int w = (int)std::min<size_t>(GPI_MAX_WARPS, (size_t)max_smem / per_warp);
-        if (w < 1) return;
+        if (w < 1 || blob > (size_t)max_smem) return;
         // score: instances resident per SM, then fewer lanes per instance (less shuffle traffic)
         const int inst = w * Cfg::IPW, binst = best.warps * (best.L ? 32 / best.L : 0);
         const bool better = best.L == 0 || (w >= 4 && best.warps < 4) || (((w >= 4) == (best.warps >= 4)) && inst > binst);
         if (better) {
             best.L = L;
             best.warps = w;
-            best.smem = per_warp * w;
+            best.smem = std::max(per_warp * (size_t)w, blob);
         }
     }
 }

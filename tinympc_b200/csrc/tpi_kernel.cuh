@@ -287,50 +287,40 @@ __global__ void __launch_bounds__(TPI_THREADS, (sizeof(T) == 4 && !EXT) ? 4 : 2)
         for (int k = N - 2; k >= 0; --k) {
             T q[NX], r[NU];
             {
-                T xr[NX], vn[NX], g[NX];
+                // every global load of this step is issued before the first use (a thread has no other way to overlap
+                // them: one dependent load round costs ~1 us and the EXT path used to have five per step)
+                T xr[NX], vn[NX], g[NX], ur[NU], zn[NU], y[NU];
+                T ev[EXT ? 3 : 1][NX], eg[EXT ? 3 : 1][NX], ez[EXT ? 3 : 1][NU], ey[EXT ? 3 : 1][NU];
                 load_col<T, NX>(xrefp + (int64_t)k * NX, xr);
-                if (zin) { zero(vn); zero(g); } else { SX::load(P.w_v[c], k, S, b, vn); SX::load(P.w_g, k, S, b, g); }
+                if (urefp) load_col<T, NU>(urefp + (int64_t)k * NU, ur); else zero(ur);
+                if (zin) { zero(vn); zero(g); zero(zn); zero(y); } else {
+                    SX::load(P.w_v[c], k, S, b, vn); SX::load(P.w_g, k, S, b, g);
+                    SU::load(P.w_z[c], k, S, b, zn); SU::load(P.w_y, k, S, b, y);
+                }
+                if constexpr (EXT) {
+                    if (P.soc_x) { SX::load(P.w_vc, k, S, b, ev[0]); SX::load(P.w_gc, k, S, b, eg[0]); }
+                    if (P.lin_x) { SX::load(P.w_vl, k, S, b, ev[1]); SX::load(P.w_gl, k, S, b, eg[1]); }
+                    if (P.tvl_x) { SX::load(P.w_vlt, k, S, b, ev[2]); SX::load(P.w_glt, k, S, b, eg[2]); }
+                    if (P.soc_u) { SU::load(P.w_zc, k, S, b, ez[0]); SU::load(P.w_yc, k, S, b, ey[0]); }
+                    if (P.lin_u) { SU::load(P.w_zl, k, S, b, ez[1]); SU::load(P.w_yl, k, S, b, ey[1]); }
+                    if (P.tvl_u) { SU::load(P.w_zlt, k, S, b, ez[2]); SU::load(P.w_ylt, k, S, b, ey[2]); }
+                }
 #pragma unroll
                 for (int i = 0; i < NX; ++i) q[i] = nmac<FAST>(-(xr[i] * P.Qd[i]), rho, vn[i] - g[i]);
-                if constexpr (EXT) {
-                    if (P.soc_x) {
-                        SX::load(P.w_vc, k, S, b, vn); SX::load(P.w_gc, k, S, b, g);
-#pragma unroll
-                        for (int i = 0; i < NX; ++i) q[i] = nmac<FAST>(q[i], rho, vn[i] - g[i]);
-                    }
-                    if (P.lin_x) {
-                        SX::load(P.w_vl, k, S, b, vn); SX::load(P.w_gl, k, S, b, g);
-#pragma unroll
-                        for (int i = 0; i < NX; ++i) q[i] = nmac<FAST>(q[i], rho, vn[i] - g[i]);
-                    }
-                    if (P.tvl_x) {
-                        SX::load(P.w_vlt, k, S, b, vn); SX::load(P.w_glt, k, S, b, g);
-#pragma unroll
-                        for (int i = 0; i < NX; ++i) q[i] = nmac<FAST>(q[i], rho, vn[i] - g[i]);
-                    }
-                }
-            }
-            {
-                T ur[NU], zn[NU], y[NU];
-                if (urefp) load_col<T, NU>(urefp + (int64_t)k * NU, ur); else zero(ur);
-                if (zin) { zero(zn); zero(y); } else { SU::load(P.w_z[c], k, S, b, zn); SU::load(P.w_y, k, S, b, y); }
 #pragma unroll
                 for (int j = 0; j < NU; ++j) r[j] = nmac<FAST>(-(ur[j] * P.Rd[j]), rho, zn[j] - y[j]);
                 if constexpr (EXT) {
-                    if (P.soc_u) {
-                        SU::load(P.w_zc, k, S, b, zn); SU::load(P.w_yc, k, S, b, y);
+                    const bool fx[3] = {P.soc_x != 0, P.lin_x != 0, P.tvl_x != 0}, fu[3] = {P.soc_u != 0, P.lin_u != 0, P.tvl_u != 0};
 #pragma unroll
-                        for (int j = 0; j < NU; ++j) r[j] = nmac<FAST>(r[j], rho, zn[j] - y[j]);
-                    }
-                    if (P.lin_u) {
-                        SU::load(P.w_zl, k, S, b, zn); SU::load(P.w_yl, k, S, b, y);
+                    for (int t = 0; t < 3; ++t) {  // admm.cpp:268-276 / :281-289, in the reference's order
+                        if (fx[t]) {
 #pragma unroll
-                        for (int j = 0; j < NU; ++j) r[j] = nmac<FAST>(r[j], rho, zn[j] - y[j]);
-                    }
-                    if (P.tvl_u) {
-                        SU::load(P.w_zlt, k, S, b, zn); SU::load(P.w_ylt, k, S, b, y);
+                            for (int i = 0; i < NX; ++i) q[i] = nmac<FAST>(q[i], rho, ev[t][i] - eg[t][i]);
+                        }
+                        if (fu[t]) {
 #pragma unroll
-                        for (int j = 0; j < NU; ++j) r[j] = nmac<FAST>(r[j], rho, zn[j] - y[j]);
+                            for (int j = 0; j < NU; ++j) r[j] = nmac<FAST>(r[j], rho, ez[t][j] - ey[t][j]);
+                        }
                     }
                 }
             }
@@ -355,9 +345,26 @@ __global__ void __launch_bounds__(TPI_THREADS, (sizeof(T) == 4 && !EXT) ? 4 : 2)
         for (int i = 0; i < NX; ++i) x[i] = x0[i];
         T rpx = T(0), rdx = T(0), rpu = T(0), rdu = T(0);
         for (int k = 0; k < N; ++k) {
+            // all global loads of the column first (state part, then — if the column has inputs — the input part)
+            T g[NX], vo[NX], vn[NX], d[NU], y[NU], zo[NU];
+            T egx[EXT ? 3 : 1][NX], eyu[EXT ? 3 : 1][NU];
+            const bool hasu = k < N - 1;
+            if (zin) { zero(g); zero(vo); zero(y); zero(zo); } else {
+                SX::load(P.w_g, k, S, b, g); SX::load(P.w_v[vs], k, S, b, vo);
+                if (hasu) { SU::load(P.w_y, k, S, b, y); SU::load(P.w_z[vs], k, S, b, zo); }
+            }
+            if (hasu) SU::load(P.w_d, k, S, b, d);
+            if constexpr (EXT) {
+                if (P.soc_x) SX::load(P.w_gc, k, S, b, egx[0]);
+                if (P.lin_x) SX::load(P.w_gl, k, S, b, egx[1]);
+                if (P.tvl_x) SX::load(P.w_glt, k, S, b, egx[2]);
+                if (hasu) {
+                    if (P.soc_u) SU::load(P.w_yc, k, S, b, eyu[0]);
+                    if (P.lin_u) SU::load(P.w_yl, k, S, b, eyu[1]);
+                    if (P.tvl_u) SU::load(P.w_ylt, k, S, b, eyu[2]);
+                }
+            }
             {   // state column k
-                T g[NX], vo[NX], vn[NX];
-                if (zin) { zero(g); zero(vo); } else { SX::load(P.w_g, k, S, b, g); SX::load(P.w_v[vs], k, S, b, vo); }
                 auto upd_x = [&](auto lo, auto hi) {  // vnew = clamp(x + g); g += x - vnew; residual maxima
 #pragma unroll
                     for (int i = 0; i < NX; ++i) {
@@ -376,8 +383,8 @@ __global__ void __launch_bounds__(TPI_THREADS, (sizeof(T) == 4 && !EXT) ? 4 : 2)
                 SX::store(P.w_g, k, S, b, g);
                 if constexpr (EXT) {
                     if (P.soc_x) {
-                        T gc[NX], vc[NX];
-                        SX::load(P.w_gc, k, S, b, gc);
+                        T(&gc)[NX] = egx[0];
+                        T vc[NX];
 #pragma unroll
                         for (int i = 0; i < NX; ++i) vc[i] = x[i] + gc[i];
                         soc_cols<T, NX>(vc, P.ncx, P.cone_x_start, P.cone_x_mu);
@@ -387,8 +394,8 @@ __global__ void __launch_bounds__(TPI_THREADS, (sizeof(T) == 4 && !EXT) ? 4 : 2)
                         SX::store(P.w_gc, k, S, b, gc);
                     }
                     if (P.lin_x) {
-                        T gl[NX], vl[NX];
-                        SX::load(P.w_gl, k, S, b, gl);
+                        T(&gl)[NX] = egx[1];
+                        T vl[NX];
 #pragma unroll
                         for (int i = 0; i < NX; ++i) vl[i] = x[i] + gl[i];
                         project_rows<FAST, T, NX>(vl, P.Alin_x, P.nlx, 0, P.nlx, P.blin_x);
@@ -398,8 +405,8 @@ __global__ void __launch_bounds__(TPI_THREADS, (sizeof(T) == 4 && !EXT) ? 4 : 2)
                         SX::store(P.w_gl, k, S, b, gl);
                     }
                     if (P.tvl_x) {
-                        T gl[NX], vl[NX];
-                        SX::load(P.w_glt, k, S, b, gl);
+                        T(&gl)[NX] = egx[2];
+                        T vl[NX];
 #pragma unroll
                         for (int i = 0; i < NX; ++i) vl[i] = x[i] + gl[i];
                         project_rows<FAST, T, NX>(vl, P.tv_Alin_x, P.ntvx * N, P.ntvx * k, P.ntvx, P.tv_blin_x + (int64_t)k * P.ntvx);
@@ -410,10 +417,8 @@ __global__ void __launch_bounds__(TPI_THREADS, (sizeof(T) == 4 && !EXT) ? 4 : 2)
                     }
                 }
             }
-            if (k < N - 1) {  // input column k and the rollout step
-                T d[NU], y[NU], zo[NU], u[NU], zn[NU];
-                SU::load(P.w_d, k, S, b, d);
-                if (zin) { zero(y); zero(zo); } else { SU::load(P.w_y, k, S, b, y); SU::load(P.w_z[vs], k, S, b, zo); }
+            if (hasu) {  // input column k and the rollout step
+                T u[NU], zn[NU];
                 {   // u_k = -(Kinf x_k) - d_k                                              (admm.cpp:29)
                     T kx[NU];
                     dots_f<FAST, NU, NX>([&](int j, int m) { return P.Kinf[j + NU * m]; }, x, kx);
@@ -438,8 +443,8 @@ __global__ void __launch_bounds__(TPI_THREADS, (sizeof(T) == 4 && !EXT) ? 4 : 2)
                 SU::store(P.w_y, k, S, b, y);
                 if constexpr (EXT) {
                     if (P.soc_u) {
-                        T yc[NU], zc[NU];
-                        SU::load(P.w_yc, k, S, b, yc);
+                        T(&yc)[NU] = eyu[0];
+                        T zc[NU];
 #pragma unroll
                         for (int j = 0; j < NU; ++j) zc[j] = u[j] + yc[j];
                         soc_cols<T, NU>(zc, P.ncu, P.cone_u_start, P.cone_u_mu);
@@ -449,8 +454,8 @@ __global__ void __launch_bounds__(TPI_THREADS, (sizeof(T) == 4 && !EXT) ? 4 : 2)
                         SU::store(P.w_yc, k, S, b, yc);
                     }
                     if (P.lin_u) {
-                        T yl[NU], zl[NU];
-                        SU::load(P.w_yl, k, S, b, yl);
+                        T(&yl)[NU] = eyu[1];
+                        T zl[NU];
 #pragma unroll
                         for (int j = 0; j < NU; ++j) zl[j] = u[j] + yl[j];
                         project_rows<FAST, T, NU>(zl, P.Alin_u, P.nlu, 0, P.nlu, P.blin_u);
@@ -460,8 +465,8 @@ __global__ void __launch_bounds__(TPI_THREADS, (sizeof(T) == 4 && !EXT) ? 4 : 2)
                         SU::store(P.w_yl, k, S, b, yl);
                     }
                     if (P.tvl_u) {
-                        T yl[NU], zl[NU];
-                        SU::load(P.w_ylt, k, S, b, yl);
+                        T(&yl)[NU] = eyu[2];
+                        T zl[NU];
 #pragma unroll
                         for (int j = 0; j < NU; ++j) zl[j] = u[j] + yl[j];
                         project_rows<FAST, T, NU>(zl, P.tv_Alin_u, P.ntvu * (N - 1), P.ntvu * k, P.ntvu, P.tv_blin_u + (int64_t)k * P.ntvu);

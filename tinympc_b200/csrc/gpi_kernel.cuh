@@ -750,15 +750,15 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
             cost_eval(xr, ur, pa, pb, q, r);
         }
         gather_u(r, Rf);
-        for (int k = N - 2; k >= 0; --k) {
-            // next column's cost inputs (independent of p): issued now, consumed at the end of this step
+        // one backward step; MORE = another column follows (its cost inputs are fetched now and consumed at the end of
+        // the step).  The last step (k = 0) is peeled so that the loop body carries no k > 0 predicates.
+        auto bwd_step = [&](int k, const bool MORE) {  // always inlined with a literal MORE
             T xr_n[RX], ur_n[RU], pa_n[PVP], pb_n[PVP];
-            const int kn = (k > 0) ? k - 1 : 0;  // clamped: the k = 0 step re-reads column 0 and discards it
-            if (k > 0) {
+            if (MORE) {
                 xp -= NX;
                 if (has_uref) up -= NU;
+                cost_load(k - 1, xp, up, xr_n, ur_n, pa_n, pb_n);
             }
-            cost_load(kn, xp, up, xr_n, ur_n, pa_n, pb_n);
             // d_k = Quu_inv ((B^T p_{k+1} + r_k) + BPf)
             T s_[RU], Sf[NU], acc1[RX + RU], kr[RX], dq[RU];
             dots<FAST>(mS1b, Pf, acc1);  // [AmBKt p_{k+1} ; B^T p_{k+1}]
@@ -769,14 +769,18 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
             dots<FAST>(mKt, Rf, kr);
 #pragma unroll
             for (int a = 0; a < RX; ++a) po[a] = ((q[a] + acc1[a]) - kr[a]) + vAPf[a];
-            gather_x(po, Pf);
+            if (MORE) gather_x(po, Pf);  // p_0 itself is never used (the forward pass starts from x_0)
             dots<FAST>(mQuu, Sf, dq);
 #pragma unroll
             for (int b = 0; b < RU; ++b)
                 if (busy && uv[b]) sts(aD + (unsigned)k * DSTR + (unsigned)(b * 32) * ES, dq[b]);
-            cost_eval(xr_n, ur_n, pa_n, pb_n, q, r);
-            gather_u(r, Rf);
-        }
+            if (MORE) {
+                cost_eval(xr_n, ur_n, pa_n, pb_n, q, r);
+                gather_u(r, Rf);
+            }
+        };
+        for (int k = N - 2; k >= 1; --k) bwd_step(k, true);
+        bwd_step(0, false);
         __syncwarp();
 
         T rpx = T(0), rdx = T(0), rpu = T(0), rdu = T(0);

@@ -163,6 +163,12 @@ typedef struct tinympc_batch {
     int32_t *solved; /* [B] solution->solved (tiny_solve returns !solved)            */
     void *residuals; /* [B][4]: primal_state, dual_state, primal_input, dual_input (types.hpp:202-205); may be NULL */
     void *u0;        /* [B][nu] optional: work->u.col(0), the control every example applies (e.g. quadrotor_hovering.cpp:92) */
+    /* Heterogeneous batch (optional): one model + cache per instance instead of the handle's shared one.
+     * [B][tinympc_b200_model_blob_elems(nx,nu)] elements of the problem dtype, each blob =
+     *   Adyn | Bdyn | fdyn | Q | R | Kinf | Pinf | Quu_inv | AmBKt | APf | BPf | rho      (column-major pieces, as in
+     * tinympc_problem_t); build it with tinympc_b200_precompute_cache_batch.  Bounds / settings stay shared.
+     * Served by the on-chip (GPI) kernel only: box constraints, horizons that fit in shared memory. */
+    const void *models;
 } tinympc_batch_t;
 
 typedef struct tinympc_b200_solver tinympc_b200_solver_t;
@@ -195,6 +201,21 @@ int tinympc_b200_default_settings(tinympc_settings_t *s);
 int tinympc_b200_precompute_cache(int32_t dtype, int32_t nx, int32_t nu, double rho, const void *Adyn,
                                   const void *Bdyn, const void *fdyn, const void *Q, const void *R, void *Kinf,
                                   void *Pinf, void *Quu_inv, void *AmBKt, void *APf, void *BPf);
+
+/* number of elements of one per-instance model blob (see tinympc_batch_t.models) */
+int64_t tinympc_b200_model_blob_elems(int32_t nx, int32_t nu);
+
+/*
+ * tiny_setup's arithmetic for B different models at once, on the host with `nthreads` threads: for instance b
+ *   Q_b = Qdiag[b] + rho[b], R_b = Rdiag[b] + rho[b]            (tiny_api.cpp:117-118)
+ *   cache_b = tiny_precompute_and_set_cache(A[b], B[b], f[b], Q_b, R_b, rho[b])   (tiny_api.cpp:307-381)
+ * packed into models_out[b] (layout: tinympc_batch_t.models).  A [B][nx*nx], Bm [B][nx*nu] column-major, f [B][nx],
+ * Qdiag [B][nx], Rdiag [B][nu] (the USER's diagonals, without rho), rho [B]; all in `dtype`.
+ * Returns 0, or the (1-based) index of the first instance whose Riccati recursion hit a singular matrix, negated.
+ */
+int tinympc_b200_precompute_cache_batch(int32_t dtype, int32_t nx, int32_t nu, int64_t B, const void *A, const void *Bm,
+                                        const void *f, const void *Qdiag, const void *Rdiag, const void *rho,
+                                        void *models_out, int32_t nthreads);
 
 /* tiny_setup (tiny_api.hpp:10-12) minus the precompute: uploads the problem to `device`. */
 int tinympc_b200_create(const tinympc_problem_t *problem, int32_t device, tinympc_b200_solver_t **out);

@@ -86,3 +86,24 @@ def test_product_precompute_matches_oracle_port():
         for f in ("Q", "R", "Kinf", "Pinf", "Quu_inv", "AmBKt", "APf", "BPf"):
             a, b = getattr(mine, f), getattr(ref, f)
             assert np.allclose(a, b, rtol=tol, atol=tol * max(1.0, float(np.abs(b).max()))), (name, f)
+
+
+def test_batched_precompute_equals_per_instance_precompute():
+    """tinympc_b200_precompute_cache_batch packs, per instance, exactly what the single-model precompute returns."""
+    from tinympc_b200 import workloads as wl
+    from tinympc_b200.solver import setup_models, setup_problem, unpack_model
+
+    nx, nu, N = 8, 2, 10
+    specs = [wl.random_lti(nx, nu, N, seed=100 + i) for i in range(7)]
+    for dt in (np.float64, np.float32):
+        blobs = setup_models(nx, nu, np.stack([s.A for s in specs]), np.stack([s.B for s in specs]), np.stack([s.f for s in specs]),
+                             np.stack([s.Qdiag for s in specs]), np.stack([s.Rdiag for s in specs]),
+                             np.array([0.5 + 0.25 * i for i in range(7)]), dtype=dt, nthreads=3)
+        assert blobs.shape == (7, 3 * nx * nx + 2 * nx * nu + nu * nu + 3 * nx + 2 * nu + 1)
+        for i, sp in enumerate(specs):
+            sp.rho = 0.5 + 0.25 * i
+            one = setup_problem(sp, dt)
+            m = unpack_model(blobs[i], nx, nu)
+            for f in ("A", "B", "f", "Q", "R", "Kinf", "Pinf", "Quu_inv", "AmBKt", "APf", "BPf"):
+                assert np.array_equal(np.asarray(getattr(one, f)), m[f]), (i, f)
+            assert m["rho"] == float(dt(sp.rho))

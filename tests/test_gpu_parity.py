@@ -359,3 +359,42 @@ def test_tiny_horizons(N, kernel):
     o = _port(prob, st, inst["x0"], inst["Xref"], None, None, True, want, nthreads=1)
     for key in H.OUT_KEYS + H.BOX_STATE:
         assert H.bits_equal(g[key], o[key]), (N, key)
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_heterogeneous_models_per_instance(dt):
+    """every instance has its own (A, B, Q, R, rho) and cache (tinympc_batch_t.models); the on-chip kernel keeps
+    each instance's matrix rows in its lane group's registers.  Checked against the oracle solving each model separately."""
+    from tinympc_b200.problem import MPCProblem
+    from tinympc_b200.solver import setup_models, unpack_model
+
+    nx, nu, N, Bn = 12, 4, 20, 45
+    specs = [wl.random_lti(nx, nu, N, seed=300 + i) for i in range(Bn)]
+    rhos = np.array([0.5 + 0.1 * (i % 9) for i in range(Bn)])
+    blobs = setup_models(nx, nu, np.stack([s.A for s in specs]), np.stack([s.B for s in specs]), np.stack([s.f for s in specs]),
+                         np.stack([s.Qdiag for s in specs]), np.stack([s.Rdiag for s in specs]), rhos, dtype=dt)
+    cons = specs[0].constraints
+    st = abi.Settings.from_buffer_copy(specs[0].settings)
+    st.max_iter = 40
+    probs = []
+    for i in range(Bn):
+        m = unpack_model(blobs[i], nx, nu)
+        rho = m.pop("rho")
+        probs.append(MPCProblem(nx=nx, nu=nu, N=N, dtype=dt, rho=rho, **m, **cons))
+    inst = wl.random_instances(Bn, nx, N, seed=9, dtype=dt)
+    inst["x0"] = (2.0 * inst["x0"]).astype(dt)
+    solver = _mk_solver(probs[0], st, "auto")
+    want = tuple(H.BOX_STATE)
+    g = solver.solve(inst["x0"], inst["Xref"], None, cold_start=True, want_state=want, models=blobs)
+    assert solver.stats()["kernel_family"] == abi.KERNEL_GPI
+    for i in range(Bn):
+        o = _port(probs[i], st, inst["x0"][i:i + 1], inst["Xref"], None, None, True, want, nthreads=1)
+        for key in H.OUT_KEYS + H.BOX_STATE:
+            assert H.bits_equal(g[key][i:i + 1], o[key]), (i, key)
+    assert len(set(g["iter"].tolist())) > 3  # the models really behave differently
+    # the streaming kernel cannot hold per-instance matrices: explicit request is refused loudly
+    from tinympc_b200._lib import TinyMPCError
+    s2 = _mk_solver(probs[0], st, "tpi")
+    with pytest.raises(TinyMPCError) as e:
+        s2.solve(inst["x0"], inst["Xref"], None, cold_start=True, models=blobs)
+    assert e.value.code == abi.ERR_UNSUPPORTED

@@ -38,6 +38,8 @@ def load():
     lib.tinympc_b200_version.restype = C.c_char_p
     lib.tinympc_b200_default_settings.argtypes = [C.POINTER(abi.Settings)]
     lib.tinympc_b200_precompute_cache.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_double] + [vp] * 11
+    lib.tinympc_b200_model_blob_elems.argtypes = [C.c_int32, C.c_int32]
+    lib.tinympc_b200_precompute_cache_batch.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int64] + [vp] * 7 + [C.c_int32]
     lib.tinympc_b200_create.argtypes = [C.POINTER(abi.Problem), C.c_int32, C.POINTER(vp)]
     lib.tinympc_b200_destroy.argtypes = [vp]
     lib.tinympc_b200_update_settings.argtypes = [vp, C.POINTER(abi.Settings)]
@@ -51,6 +53,7 @@ def load():
     for n in abi.EXPORTS:
         if n not in ("tinympc_b200_last_error", "tinympc_b200_version"):
             getattr(lib, n).restype = C.c_int
+    lib.tinympc_b200_model_blob_elems.restype = C.c_int64
     _lib = lib
     return lib
 

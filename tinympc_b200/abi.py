@@ -68,6 +68,7 @@ class Batch(C.Structure):
         ("sol_x", vp), ("sol_u", vp),
         ("iter", vp), ("solved", vp), ("residuals", vp),
         ("u0", vp),
+        ("models", vp),
     ]
 
 
@@ -86,6 +87,8 @@ class Stats(C.Structure):
 EXPORTS = [
     "tinympc_b200_default_settings",
     "tinympc_b200_precompute_cache",
+    "tinympc_b200_model_blob_elems",
+    "tinympc_b200_precompute_cache_batch",
     "tinympc_b200_create",
     "tinympc_b200_destroy",
     "tinympc_b200_update_settings",

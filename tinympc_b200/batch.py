@@ -15,7 +15,7 @@ class HostBatch:
     """Owns the numpy buffers of one batched solve and the ctypes struct pointing at them."""
 
     def __init__(self, prob: MPCProblem, x0, Xref, Uref=None, state: dict | None = None, cold_start=True,
-                 want_state=(), want_residuals=True):
+                 want_state=(), want_residuals=True, models=None):
         dt = prob.dtype
         nx, nu, N = prob.nx, prob.nu, prob.N
         self.prob = prob
@@ -44,6 +44,7 @@ class HostBatch:
             elif name in want_state:
                 self.state[name] = np.zeros(shape, dtype=dt)
         self.cold_start = bool(cold_start)
+        self.models = None if models is None else np.ascontiguousarray(models, dtype=dt).reshape(B, -1)
         self.sol_x = np.zeros((B, N, nx), dtype=dt)
         self.sol_u = np.zeros((B, N - 1, nu), dtype=dt)
         self.iter = np.zeros(B, dtype=np.int32)
@@ -66,6 +67,7 @@ class HostBatch:
         b.iter = self.iter.ctypes.data
         b.solved = self.solved.ctypes.data
         b.residuals = None if self.residuals is None else self.residuals.ctypes.data
+        b.models = None if self.models is None else self.models.ctypes.data
         b._owner = self
         return b
 

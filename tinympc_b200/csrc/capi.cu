@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "host_precompute.h"
@@ -297,6 +298,7 @@ tinympc_batch_t slice_batch(const tinympc_b200_solver *s, const tinympc_batch_t 
     o.solved = (int32_t *)adv(io.solved, sizeof(int32_t));
     o.residuals = adv(io.residuals, 4 * es);
     o.u0 = adv(io.u0, es * s->nu);
+    o.models = adv(io.models, es * (size_t)tinympc_b200_model_blob_elems(s->nx, s->nu));
     return o;
 }
 
@@ -319,7 +321,12 @@ int enqueue(tinympc_b200_solver *s, const tinympc_batch_t *io, cudaStream_t stre
     if (io->B <= 0) return TINYMPC_OK;
     const Features ft = features(s);
     int smem = 0;
-    const int family = resolve_family(s, ft, &smem, io->B);
+    int family = resolve_family(s, ft, &smem, io->B);
+    if (io->models) {  // per-instance models: on-chip kernel only
+        if (ft.ext || smem <= 0 || s->family == TINYMPC_KERNEL_TPI)
+            return fail(TINYMPC_ERR_UNSUPPORTED, "per-instance models need the GPI kernel (box constraints, horizon fitting in shared memory)");
+        family = TINYMPC_KERNEL_GPI;
+    }
     if (family < 0) return fail(TINYMPC_ERR_UNSUPPORTED, "GPI kernel requested but it does not support this problem (features or shared-memory footprint)");
     int64_t launches = 0, ctas = 0;
     tmpc::LaunchDesc d;
@@ -417,6 +424,44 @@ int enqueue(tinympc_b200_solver *s, const tinympc_batch_t *io, cudaStream_t stre
 
 }  // namespace
 
+namespace {
+template <typename T>
+int precompute_batch_T(int nx, int nu, int64_t B, const T *A, const T *Bm, const T *f, const T *Qd, const T *Rd, const T *rho,
+                       T *out, int nthreads) {
+    const int64_t M = tinympc_b200_model_blob_elems(nx, nu);
+    nthreads = (int)std::max<int64_t>(1, std::min<int64_t>(nthreads, B));
+    std::vector<int64_t> bad(nthreads, 0);
+    auto work = [&](int t) {
+        std::vector<T> Qw(nx), Rw(nu);
+        for (int64_t b = t; b < B; b += nthreads) {
+            const T *Ab = A + b * nx * nx, *Bb = Bm + b * nx * nu, *fb = f + b * nx;
+            T *o = out + b * M;
+            T *oA = o, *oB = oA + nx * nx, *oF = oB + nx * nu, *oQ = oF + nx, *oR = oQ + nx, *oK = oR + nu, *oP = oK + nu * nx,
+              *oQuu = oP + nx * nx, *oAm = oQuu + nu * nu, *oAPf = oAm + nx * nx, *oBPf = oAPf + nx;
+            const T r = rho[b];
+            for (int i = 0; i < nx; ++i) Qw[i] = Qd[b * nx + i] + r;  // tiny_api.cpp:117
+            for (int j = 0; j < nu; ++j) Rw[j] = Rd[b * nu + j] + r;  // tiny_api.cpp:118
+            std::copy(Ab, Ab + nx * nx, oA);
+            std::copy(Bb, Bb + nx * nu, oB);
+            std::copy(fb, fb + nx, oF);
+            std::copy(Qw.begin(), Qw.end(), oQ);
+            std::copy(Rw.begin(), Rw.end(), oR);
+            const int rc = tmpc::precompute_cache<T>(nx, nu, (double)r, Ab, Bb, fb, Qw.data(), Rw.data(), oK, oP, oQuu, oAm, oAPf, oBPf);
+            oBPf[nu] = r;
+            if (rc < 0 && bad[t] == 0) bad[t] = b + 1;
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nthreads; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto &x : th) x.join();
+    int64_t first = 0;
+    for (int64_t v : bad)
+        if (v && (!first || v < first)) first = v;
+    return first ? -(int)first : 0;
+}
+}  // namespace
+
 extern "C" {
 
 const char *tinympc_b200_last_error(void) { return g_err.c_str(); }
@@ -461,6 +506,24 @@ int tinympc_b200_precompute_cache(int32_t dtype, int32_t nx, int32_t nu, double 
         return fail(TINYMPC_ERR_ARG, "bad dtype");
     if (rc < 0) return fail(TINYMPC_ERR_ARG, "singular R + B'PB in the Riccati recursion");
     return rc;
+}
+
+int64_t tinympc_b200_model_blob_elems(int32_t nx, int32_t nu) {
+    return (int64_t)3 * nx * nx + 2 * nx * nu + nu * nu + 3 * nx + 2 * nu + 1;
+}
+
+int tinympc_b200_precompute_cache_batch(int32_t dtype, int32_t nx, int32_t nu, int64_t B, const void *A, const void *Bm,
+                                        const void *f, const void *Qdiag, const void *Rdiag, const void *rho,
+                                        void *models_out, int32_t nthreads) {
+    if (!A || !Bm || !f || !Qdiag || !Rdiag || !rho || !models_out || nx <= 0 || nu <= 0 || B < 0)
+        return fail(TINYMPC_ERR_ARG, "null pointer or bad size");
+    if (dtype == TINYMPC_F64)
+        return precompute_batch_T<double>(nx, nu, B, (const double *)A, (const double *)Bm, (const double *)f, (const double *)Qdiag,
+                                          (const double *)Rdiag, (const double *)rho, (double *)models_out, nthreads);
+    if (dtype == TINYMPC_F32)
+        return precompute_batch_T<float>(nx, nu, B, (const float *)A, (const float *)Bm, (const float *)f, (const float *)Qdiag,
+                                         (const float *)Rdiag, (const float *)rho, (float *)models_out, nthreads);
+    return fail(TINYMPC_ERR_ARG, "bad dtype");
 }
 
 int tinympc_b200_create(const tinympc_problem_t *p, int32_t device, tinympc_b200_solver_t **out) {
@@ -692,6 +755,7 @@ int tinympc_b200_solve_host(tinympc_b200_solver_t *s, const tinympc_batch_t *io)
     fields.push_back({io->x0, nullptr, es * s->nx, true, false, (void **)&dev.x0});
     if (io->xref_per_instance) fields.push_back({io->Xref, nullptr, bx, true, false, (void **)&dev.Xref});
     if (io->Uref && io->uref_per_instance) fields.push_back({io->Uref, nullptr, bu, true, false, (void **)&dev.Uref});
+    if (io->models) fields.push_back({io->models, nullptr, es * (size_t)tinympc_b200_model_blob_elems(s->nx, s->nu), true, false, (void **)&dev.models});
     {
         size_t need = (io->xref_per_instance ? 0 : bx) + ((io->Uref && !io->uref_per_instance) ? bu : 0);
         if (need) {

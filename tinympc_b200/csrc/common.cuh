@@ -207,6 +207,7 @@ struct KParams {
     int32_t *iter, *solved;
     T *residuals;
     T *u0;  // [B][nu] first rollout input, may be null
+    const T *models;  // GPI: per-instance cache blobs [B][blob+1] (A,B,f,Qd,Rd,Kinf,Pinf,Quu,AmBKt,APf,BPf,rho) or null
     T *gpi_vscratch;  // GPI: [B][N][L][PVP] copy of the previous primal pack (work->v / work->z) while v,z are persisted
     // TPI workspace (structure-of-arrays, 16-byte vectors, [k][vec][Bpad])
     void *w_v[2], *w_z[2], *w_g, *w_y, *w_d;

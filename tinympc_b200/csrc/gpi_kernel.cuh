@@ -107,7 +107,7 @@ __device__ __forceinline__ T clamp_box(T v, T lo, T hi) {
 __device__ __forceinline__ float absmax(float m, float d) { return fmaxf(m, fabsf(d)); }
 __device__ __forceinline__ double absmax(double m, double d) { return fmax(m, fabs(d)); }
 
-template <typename T, int NX, int NU, int L, bool FAST>
+template <typename T, int NX, int NU, int L, bool FAST, bool HET>
 __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
     gpi_solve_kernel(const __grid_constant__ KParams<T, NX, NU> P, const T *__restrict__ gmat, unsigned long long *queue) {
     using Cfg = GpiCfg<NX, NU, L, (int)sizeof(T)>;
@@ -120,7 +120,13 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int l = lane % L;     // lane inside the instance group
     const int slot = lane / L;  // which of the warp's instances
-    const T rho = P.rho;
+    // HET = heterogeneous batch (tinympc_batch_t.models): every instance brings its own model / cache blob and rho;
+    // the homogeneous kernel keeps rho a launch constant and its matrix rows immutable registers.
+    T rho_m = P.rho;
+    auto rho_ = [&]() -> T {
+        if constexpr (HET) return rho_m;
+        else return P.rho;
+    };
 
     // ---- stage the cache blob (A, B, f, Qd, Rd, Kinf, Pinf, Quu, AmBKt, APf, BPf) into shared memory with
     // one TMA bulk copy per CTA, then pull this lane's rows into registers.  The staging area aliases the
@@ -162,39 +168,43 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
     T mQuu[RU][NU], vRd[RU], vBPf[RU];
     bool xv[RX], uv[RU];  // row validity (padding rows compute zeros)
 #pragma unroll
-    for (int a = 0; a < RX; ++a) {
-        const int i = l * RX + a;
-        xv[a] = EXACT || (i < NX);
-        const int ii = xv[a] ? i : 0;
+    for (int a = 0; a < RX; ++a) xv[a] = EXACT || (l * RX + a < NX);
 #pragma unroll
-        for (int m = 0; m < NX; ++m) {
-            mS1b[a][m] = xv[a] ? stage[OFF_AMBKT + ii + NX * m] : T(0);
-            mS1f[a][m] = xv[a] ? stage[OFF_A + ii + NX * m] : T(0);
+    for (int b = 0; b < RU; ++b) uv[b] = EXACT || (l * RU + b < NU);
+    // `src` = a cache blob in the layout above (the staged shared-memory copy, or one instance's blob in global memory)
+    auto load_rows = [&](const T *src) {
+#pragma unroll
+        for (int a = 0; a < RX; ++a) {
+            const int ii = xv[a] ? l * RX + a : 0;
+#pragma unroll
+            for (int m = 0; m < NX; ++m) {
+                mS1b[a][m] = xv[a] ? src[OFF_AMBKT + ii + NX * m] : T(0);
+                mS1f[a][m] = xv[a] ? src[OFF_A + ii + NX * m] : T(0);
+            }
+#pragma unroll
+            for (int j = 0; j < NU; ++j) {
+                mKt[a][j] = xv[a] ? src[OFF_K + j + NU * ii] : T(0);  // Kinf^T(i,j) = Kinf(j,i)
+                mB[a][j] = xv[a] ? src[OFF_B + ii + NX * j] : T(0);
+            }
+            vQd[a] = xv[a] ? src[OFF_QD + ii] : T(0);
+            vAPf[a] = xv[a] ? src[OFF_APF + ii] : T(0);
+            vf[a] = xv[a] ? src[OFF_F + ii] : T(0);
         }
 #pragma unroll
-        for (int j = 0; j < NU; ++j) {
-            mKt[a][j] = xv[a] ? stage[OFF_K + j + NU * ii] : T(0);  // Kinf^T(i,j) = Kinf(j,i)
-            mB[a][j] = xv[a] ? stage[OFF_B + ii + NX * j] : T(0);
+        for (int b = 0; b < RU; ++b) {
+            const int jj = uv[b] ? l * RU + b : 0;
+#pragma unroll
+            for (int m = 0; m < NX; ++m) {
+                mS1b[RX + b][m] = uv[b] ? src[OFF_B + m + NX * jj] : T(0);  // B^T(j,m) = B(m,j)
+                mS1f[RX + b][m] = uv[b] ? src[OFF_K + jj + NU * m] : T(0);
+            }
+#pragma unroll
+            for (int m = 0; m < NU; ++m) mQuu[b][m] = uv[b] ? src[OFF_QUU + jj + NU * m] : T(0);
+            vRd[b] = uv[b] ? src[OFF_RD + jj] : T(0);
+            vBPf[b] = uv[b] ? src[OFF_BPF + jj] : T(0);
         }
-        vQd[a] = xv[a] ? stage[OFF_QD + ii] : T(0);
-        vAPf[a] = xv[a] ? stage[OFF_APF + ii] : T(0);
-        vf[a] = xv[a] ? stage[OFF_F + ii] : T(0);
-    }
-#pragma unroll
-    for (int b = 0; b < RU; ++b) {
-        const int j = l * RU + b;
-        uv[b] = EXACT || (j < NU);
-        const int jj = uv[b] ? j : 0;
-#pragma unroll
-        for (int m = 0; m < NX; ++m) {
-            mS1b[RX + b][m] = uv[b] ? stage[OFF_B + m + NX * jj] : T(0);  // B^T(j,m) = B(m,j)
-            mS1f[RX + b][m] = uv[b] ? stage[OFF_K + jj + NU * m] : T(0);
-        }
-#pragma unroll
-        for (int m = 0; m < NU; ++m) mQuu[b][m] = uv[b] ? stage[OFF_QUU + jj + NU * m] : T(0);
-        vRd[b] = uv[b] ? stage[OFF_RD + jj] : T(0);
-        vBPf[b] = uv[b] ? stage[OFF_BPF + jj] : T(0);
-    }
+    };
+    load_rows(stage);
     __syncthreads();  // staging area is reused as state below
 
     // ---- shared-memory state of this warp ----
@@ -311,9 +321,9 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
     };
     auto cost_eval = [&](const T (&xr)[RX], const T (&ur)[RU], const T (&pa)[PVP], const T (&pb)[PVP], T (&q)[RX], T (&r)[RU]) {
 #pragma unroll
-        for (int a = 0; a < RX; ++a) q[a] = nmac<FAST>(-(xr[a] * vQd[a]), rho, pa[a] - pb[a]);
+        for (int a = 0; a < RX; ++a) q[a] = nmac<FAST>(-(xr[a] * vQd[a]), rho_(), pa[a] - pb[a]);
 #pragma unroll
-        for (int b = 0; b < RU; ++b) r[b] = nmac<FAST>(-(ur[b] * vRd[b]), rho, pa[RX + b] - pb[RX + b]);
+        for (int b = 0; b < RU; ++b) r[b] = nmac<FAST>(-(ur[b] * vRd[b]), rho_(), pa[RX + b] - pb[RX + b]);
     };
 
     // forward pass fused with slack / dual update / residuals.  SLOW = some slot is in the first iteration of a
@@ -574,6 +584,14 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
             offu = ib * (int64_t)(N - 1) * NU;
             xrefp = P.Xref + (P.xref_pi ? offx : 0) + l * RX;
             urefp = has_uref ? P.Uref + (P.uref_pi ? offu : 0) + l * RU : P.Xref;
+            // heterogeneous batch: this instance has its own model / cache blob (same layout as the shared one, rho appended)
+            const T *pinf = P.Pinf_g;
+            if constexpr (HET) {
+                const T *mb = P.models + ib * (int64_t)(BLOB + 1);
+                load_rows(mb);
+                rho_m = mb[BLOB];
+                pinf = mb + OFF_PINF;
+            }
             // x0 (own rows) and the iteration-invariant part of the terminal cost: -(Pinf^T xref_{N-1})
             T xr[NX];
             const T *xl = xrefp - l * RX + (int64_t)(N - 1) * NX;
@@ -583,9 +601,9 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
             for (int a = 0; a < RX; ++a) {
                 const int i = l * RX + a, ii = xv[a] ? i : 0;
                 x0o[a] = xv[a] ? __ldg(P.x0 + ib * NX + ii) : T(0);
-                T sacc = xr[0] * __ldg(P.Pinf_g + 0 + NX * ii);
+                T sacc = xr[0] * __ldg(pinf + 0 + NX * ii);
 #pragma unroll
-                for (int m = 1; m < NX; ++m) sacc = mac<FAST>(sacc, xr[m], __ldg(P.Pinf_g + m + NX * ii));
+                for (int m = 1; m < NX; ++m) sacc = mac<FAST>(sacc, xr[m], __ldg(pinf + m + NX * ii));
                 pterm[a] = xv[a] ? -sacc : T(0);
             }
         }
@@ -738,7 +756,7 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
             load_pack(aPA, N - 1, pa);
             load_pack(aPB, N - 1, pb);
 #pragma unroll
-            for (int a = 0; a < RX; ++a) po[a] = nmac<FAST>(pterm[a], rho, pa[a] - pb[a]);
+            for (int a = 0; a < RX; ++a) po[a] = nmac<FAST>(pterm[a], rho_(), pa[a] - pb[a]);
         }
         gather_x(po, Pf);
         T q[RX], r[RU], Rf[NU];
@@ -797,9 +815,9 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
             it += 1;
             if (it % P.check_termination == 0) {
                 res_px = rpx;
-                res_dx = rdx * rho;
+                res_dx = rdx * rho_();
                 res_pu = rpu;
-                res_du = rdu * rho;
+                res_du = rdu * rho_();
                 if (res_px < P.pri_tol && res_pu < P.pri_tol && res_dx < P.dua_tol && res_du < P.dua_tol) solved = 1;
             }
         }
@@ -849,10 +867,10 @@ inline int gpi_fit_T(int N, int max_smem) {
     return (int)gpi_plan<T, NX, NU>(N, max_smem).smem;
 }
 
-template <typename T, int NX, int NU, int L, bool FAST>
+template <typename T, int NX, int NU, int L, bool FAST, bool HET>
 int launch_gpi_L(LaunchDesc *d, const GpiPlan &plan, const KParams<T, NX, NU> &P, const T *gmat) {
     if constexpr (gpi_feasible<T, NX, NU, L>()) {
-        auto kern = gpi_solve_kernel<T, NX, NU, L, FAST>;
+        auto kern = gpi_solve_kernel<T, NX, NU, L, FAST, HET>;
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem) != cudaSuccess)
             return TINYMPC_ERR_CUDA;
         const int64_t ngroups = (d->io.B + (32 / L) - 1) / (32 / L);

@@ -83,6 +83,7 @@ void fill_params(KParams<T, TM_NX, TM_NU> &P, const LaunchDesc &d) {
     P.sol_x = (T *)io.sol_x; P.sol_u = (T *)io.sol_u;
     P.iter = io.iter; P.solved = io.solved; P.residuals = (T *)io.residuals;
     P.u0 = (T *)io.u0;
+    P.models = (const T *)io.models;
     P.gpi_vscratch = (T *)d.gpi_vscratch;
     P.w_v[0] = d.w_v[0]; P.w_v[1] = d.w_v[1]; P.w_z[0] = d.w_z[0]; P.w_z[1] = d.w_z[1];
     P.w_g = d.w_g; P.w_y = d.w_y; P.w_d = d.w_d;
@@ -115,9 +116,14 @@ int launch_gpi(LaunchDesc *d) {
     KParams<T, NX, NU> P;
     fill_params<T>(P, *d);
     const T *gmat = (const T *)d->gmat;
-    if (plan.L == 4) return launch_gpi_L<T, NX, NU, 4, FAST>(d, plan, P, gmat);
-    if (plan.L == 8) return launch_gpi_L<T, NX, NU, 8, FAST>(d, plan, P, gmat);
-    return launch_gpi_L<T, NX, NU, 16, FAST>(d, plan, P, gmat);
+    if (d->io.models) {  // heterogeneous batch: per-instance model blobs
+        if (plan.L == 4) return launch_gpi_L<T, NX, NU, 4, FAST, true>(d, plan, P, gmat);
+        if (plan.L == 8) return launch_gpi_L<T, NX, NU, 8, FAST, true>(d, plan, P, gmat);
+        return launch_gpi_L<T, NX, NU, 16, FAST, true>(d, plan, P, gmat);
+    }
+    if (plan.L == 4) return launch_gpi_L<T, NX, NU, 4, FAST, false>(d, plan, P, gmat);
+    if (plan.L == 8) return launch_gpi_L<T, NX, NU, 8, FAST, false>(d, plan, P, gmat);
+    return launch_gpi_L<T, NX, NU, 16, FAST, false>(d, plan, P, gmat);
 }
 #endif
 
@@ -131,6 +137,7 @@ int launch_T(LaunchDesc *d) {
 #else
     if (d->family == TINYMPC_KERNEL_GPI) return TINYMPC_ERR_UNSUPPORTED;
 #endif
+    if (d->io.models) return TINYMPC_ERR_UNSUPPORTED;  // per-instance models live in the GPI kernel's per-lane registers only
     if (d->ext) return d->fast ? launch_tpi<T, true, true>(d) : launch_tpi<T, false, true>(d);
     return d->fast ? launch_tpi<T, true, false>(d) : launch_tpi<T, false, false>(d);
 }

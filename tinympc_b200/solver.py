@@ -56,6 +56,43 @@ def setup_problem(spec: ModelSpec, dtype=np.float32) -> MPCProblem:
     return p
 
 
+def setup_models(nx, nu, A, B, f, Qdiag, Rdiag, rho, dtype=np.float32, nthreads=0):
+    """tiny_setup's arithmetic for a heterogeneous batch: per-instance A [Bn,nx,nx], B [Bn,nx,nu] (row index first, like the
+    reference's examples), f [Bn,nx], user diagonals Qdiag [Bn,nx], Rdiag [Bn,nu], rho [Bn]  ->  packed model blobs
+    [Bn, blob] for BatchedTinySolver.solve(..., models=...)  (tinympc_batch_t.models)."""
+    import os
+
+    lib = load()
+    dt = np.dtype(dtype).type
+    A = np.asarray(A, dtype=dt)
+    Bn = A.shape[0]
+    A_ = np.ascontiguousarray(np.transpose(A.reshape(Bn, nx, nx), (0, 2, 1)))          # column-major per instance
+    B_ = np.ascontiguousarray(np.transpose(np.asarray(B, dtype=dt).reshape(Bn, nx, nu), (0, 2, 1)))
+    f_ = np.ascontiguousarray(np.asarray(f, dtype=dt).reshape(Bn, nx))
+    Q_ = np.ascontiguousarray(np.asarray(Qdiag, dtype=dt).reshape(Bn, nx))
+    R_ = np.ascontiguousarray(np.asarray(Rdiag, dtype=dt).reshape(Bn, nu))
+    r_ = np.ascontiguousarray(np.broadcast_to(np.asarray(rho, dtype=dt), (Bn,)))
+    M = int(lib.tinympc_b200_model_blob_elems(nx, nu))
+    out = np.zeros((Bn, M), dtype=dt)
+    vp = lambda a: C.c_void_p(a.ctypes.data)  # noqa: E731
+    check(lib.tinympc_b200_precompute_cache_batch(dtype_code(dt), nx, nu, Bn, vp(A_), vp(B_), vp(f_), vp(Q_), vp(R_), vp(r_),
+                                                  vp(out), nthreads or (os.cpu_count() or 1)))
+    return out
+
+
+def unpack_model(blob, nx, nu):
+    """One per-instance blob -> dict of column-major pieces (for building the equivalent single-model MPCProblem)."""
+    sizes = [("A", (nx, nx)), ("B", (nx, nu)), ("f", (nx,)), ("Q", (nx,)), ("R", (nu,)), ("Kinf", (nu, nx)), ("Pinf", (nx, nx)),
+             ("Quu_inv", (nu, nu)), ("AmBKt", (nx, nx)), ("APf", (nx,)), ("BPf", (nu,))]
+    out, o = {}, 0
+    for name, shp in sizes:
+        n = int(np.prod(shp))
+        out[name] = np.array(blob[o:o + n]).reshape(shp, order="F")
+        o += n
+    out["rho"] = float(blob[o])
+    return out
+
+
 class BatchedTinySolver:
     """A TinySolver (types.hpp:213-218) for B independent instances on one B200."""
 
@@ -101,8 +138,8 @@ class BatchedTinySolver:
         return {n: getattr(st, n) for n, _ in abi.Stats._fields_}
 
     # ---- host buffers (numpy): the call a reference user would make; H2D/D2H inside ------------------
-    def solve(self, x0, Xref, Uref=None, state=None, cold_start=True, want_state=()) -> dict:
-        hb = HostBatch(self.problem, x0, Xref, Uref, state=state, cold_start=cold_start, want_state=want_state)
+    def solve(self, x0, Xref, Uref=None, state=None, cold_start=True, want_state=(), models=None) -> dict:
+        hb = HostBatch(self.problem, x0, Xref, Uref, state=state, cold_start=cold_start, want_state=want_state, models=models)
         cb = hb.to_c()
         check(self._lib.tinympc_b200_solve_host(self._h, C.byref(cb)))
         return hb.result()
@@ -115,7 +152,7 @@ class BatchedTinySolver:
 
     # ---- device buffers (torch tensors on cuda:<device>) ---------------------------------------------
     def make_device_batch(self, x0, Xref, Uref=None, state=None, cold_start=True, want_state=(), want_residuals=True,
-                          want_u0=False, want_solution=True):
+                          want_u0=False, want_solution=True, models=None):
         """Allocate/adopt torch CUDA tensors and build the device-pointer tinympc_batch_t."""
         import torch
 
@@ -162,6 +199,9 @@ class BatchedTinySolver:
         b.sol_x = None if out["sol_x"] is None else out["sol_x"].data_ptr()
         b.sol_u = None if out["sol_u"] is None else out["sol_u"].data_ptr()
         b.u0 = None if out["u0"] is None else out["u0"].data_ptr()
+        models_t = None if models is None else t(models)
+        tens["models"] = models_t
+        b.models = None if models_t is None else models_t.data_ptr()
         b.iter, b.solved = out["iter"].data_ptr(), out["solved"].data_ptr()
         b.residuals = None if out["residuals"] is None else out["residuals"].data_ptr()
         res = dict(out)

@@ -185,6 +185,8 @@ typedef struct tinympc_b200_stats {
     int32_t ctas;
     int32_t threads_per_cta;
     int64_t gpi_instances; /* HYBRID: how many instances of the batch the GPI kernel took (rest: TPI) */
+    int32_t tmem_cols_per_cta; /* GPI: tensor-memory columns holding the dual variables and d (0 = all in shared memory) */
+    int32_t reserved0;
 } tinympc_b200_stats_t;
 
 /* tiny_set_default_settings (tiny_api.cpp:413-441, tiny_api_constants.hpp:5-16) */

@@ -5,6 +5,8 @@ every solution/state scalar, all four residuals, iter and solved.  FAST mode (FM
 reference's own build-to-build scatter: <= 2e-4 relative on x,u in fp32 (1e-9 in fp64), with
 iteration counts allowed to move by one termination check on a small fraction of instances.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -15,11 +17,24 @@ from tinympc_b200.solver import BatchedTinySolver, setup_problem
 
 pytestmark = pytest.mark.gpu
 
-KERNELS = {"tpi": abi.KERNEL_TPI, "gpi": abi.KERNEL_GPI, "hybrid": abi.KERNEL_HYBRID, "auto": abi.KERNEL_AUTO}
+# "gpi" = the planner's choice (dual variables + d in tensor memory when that holds more instances per SM);
+# "gpi_smem" forces the all-shared-memory variant (TINYMPC_GPI_TMEM=0)
+KERNELS = {"tpi": abi.KERNEL_TPI, "gpi": abi.KERNEL_GPI, "gpi_smem": abi.KERNEL_GPI, "hybrid": abi.KERNEL_HYBRID, "auto": abi.KERNEL_AUTO}
+
+
+@pytest.fixture(autouse=True)
+def _default_gpi_variant():
+    os.environ.pop("TINYMPC_GPI_TMEM", None)
+    yield
+    os.environ.pop("TINYMPC_GPI_TMEM", None)
 
 
 def _mk_solver(prob, st, kernel, mode=abi.MODE_STRICT):
     from tinympc_b200._lib import TinyMPCError
+    if kernel == "gpi_smem":
+        os.environ["TINYMPC_GPI_TMEM"] = "0"
+    else:
+        os.environ.pop("TINYMPC_GPI_TMEM", None)
     try:
         s = BatchedTinySolver(prob, st, device=0, mode=mode, kernel=KERNELS[kernel])
     except TinyMPCError as e:  # pragma: no cover
@@ -44,11 +59,11 @@ def _gpi_applicable(prob, st):
     return not ext
 
 
-@pytest.mark.parametrize("kernel", ["tpi", "gpi"])
+@pytest.mark.parametrize("kernel", ["tpi", "gpi", "gpi_smem"])
 @pytest.mark.parametrize("name", H.golden_names())
 def test_strict_bit_identical_to_reference_golden(name, kernel):
     prob, st, inst, meta, gold = H.load_golden(name)
-    if kernel == "gpi" and not _gpi_applicable(prob, st):
+    if kernel.startswith("gpi") and not _gpi_applicable(prob, st):
         pytest.skip("GPI kernel covers box constraints only (cones/hyperplanes run on the TPI kernel)")
     solver = _mk_solver(prob, st, kernel)
     got, _ = H.closed_loop(prob, st, inst, meta["steps"], meta["reset_duals"], meta["state"], _cuda_fn(solver),
@@ -59,7 +74,7 @@ def test_strict_bit_identical_to_reference_golden(name, kernel):
     assert solver.stats()["kernel_family"] == KERNELS[kernel]
 
 
-@pytest.mark.parametrize("kernel", ["tpi", "gpi"])
+@pytest.mark.parametrize("kernel", ["tpi", "gpi", "gpi_smem"])
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
 def test_strict_batch_vs_oracle_ragged(dt, kernel):
     """A ragged batch (B not a multiple of the warp / group size) of randomised tracking instances, cold start,
@@ -86,7 +101,7 @@ def test_strict_batch_vs_oracle_ragged(dt, kernel):
         assert H.bits_equal(g2[key], o2[key]), "warm " + key
 
 
-@pytest.mark.parametrize("kernel", ["tpi", "gpi"])
+@pytest.mark.parametrize("kernel", ["tpi", "gpi", "gpi_smem"])
 def test_edge_cases(kernel):
     """B=1, B=33; max_iter=1; check_termination=3 (stale residual fields); per-instance Uref; shared refs."""
     spec = wl.quadrotor(N=10)
@@ -106,7 +121,7 @@ def test_edge_cases(kernel):
             assert H.bits_equal(g[key], o[key]), (B, max_iter, check, key)
 
 
-@pytest.mark.parametrize("kernel", ["tpi", "gpi"])
+@pytest.mark.parametrize("kernel", ["tpi", "gpi", "gpi_smem"])
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
 def test_fast_mode_within_reference_scatter(dt, kernel):
     """FAST mode = same operation order with FMA contraction.  It cannot be bit-identical to any Eigen build
@@ -147,7 +162,7 @@ def test_fast_mode_within_reference_scatter(dt, kernel):
     assert g2["iter"].mean() <= 1.1 * o2["iter"].mean() + 0.5
 
 
-@pytest.mark.parametrize("kernel", ["tpi", "gpi"])
+@pytest.mark.parametrize("kernel", ["tpi", "gpi", "gpi_smem"])
 def test_device_pointer_path_equals_host_path(kernel):
     import torch
 
@@ -177,9 +192,15 @@ def test_full_size_identical_instances_and_shard_invariance():
     B = 65536
     inst = wl.hovering_instances(B, N=50, dtype=dt)
     o = _port(prob, st, inst["x0"][:1], inst["Xref"], None, None, True, ("u",), nthreads=1)
-    for kernel in ("gpi", "tpi", "hybrid"):
+    for kernel in ("gpi", "gpi_smem", "tpi", "hybrid"):
         solver = _mk_solver(prob, st, kernel)
         g = solver.solve(inst["x0"], inst["Xref"], None, cold_start=True, want_state=("u",))
+        if kernel.startswith("gpi"):
+            # (12,4,50) fp32: g, y and d (5 columns per knot point and thread) fit in tensor memory for 8 warps per SM,
+            # twice what shared memory alone holds
+            stt = solver.stats()
+            assert stt["tmem_cols_per_cta"] == (512 if kernel == "gpi" else 0)
+            assert stt["instances_per_cta"] == (64 if kernel == "gpi" else 32)
         for key in ("sol_x", "sol_u", "iter", "solved", "residuals", "u"):
             assert H.bits_equal(g[key][:1], o[key]), (kernel, key)
             assert (g[key] == g[key][:1]).all(), (kernel, key)
@@ -233,7 +254,7 @@ def test_errors_are_loud():
     assert e.value.code == abi.ERR_UNSUPPORTED
 
 
-@pytest.mark.parametrize("kernel", ["tpi", "gpi"])
+@pytest.mark.parametrize("kernel", ["tpi", "gpi", "gpi_smem"])
 def test_device_resident_closed_loop_matches_oracle(kernel):
     """the reference's closed loop (set x0 -> solve warm-started -> x0 = A x0 + B u0) for 300 plants kept
     entirely on the GPU (DeviceMPCLoop + tinympc_b200_advance) equals the oracle stepping the same loop on the host."""
@@ -275,7 +296,7 @@ def test_device_resident_closed_loop_matches_oracle(kernel):
         assert H.bits_equal(loop.x0.cpu().numpy(), x0), ("advance", k)
 
 
-@pytest.mark.parametrize("kernel", ["tpi", "gpi"])
+@pytest.mark.parametrize("kernel", ["tpi", "gpi", "gpi_smem"])
 @pytest.mark.parametrize("dims", [(4, 2), (4, 8), (6, 3), (8, 8), (12, 2), (12, 8), (16, 2), (16, 4), (16, 8)])
 def test_every_compiled_dimension_vs_oracle(dims, kernel):
     """Random LTI problems for the other compiled (nx, nu) pairs (lane mappings L=4 and L=8, padding rows),
@@ -298,7 +319,7 @@ def test_every_compiled_dimension_vs_oracle(dims, kernel):
         assert (np.abs(o["znew"]) >= 1.0 - 1e-6).any()  # the box was active somewhere
 
 
-@pytest.mark.parametrize("kernel", ["tpi", "gpi"])
+@pytest.mark.parametrize("kernel", ["tpi", "gpi", "gpi_smem"])
 def test_time_varying_bounds(kernel):
     """Bounds are full nx x N / nu x (N-1) matrices in the reference API (types.hpp:117-120); every example passes
     constants, here they really vary along the horizon."""
@@ -323,7 +344,7 @@ def test_time_varying_bounds(kernel):
         assert H.bits_equal(g[key], o[key]), key
 
 
-@pytest.mark.parametrize("kernel", ["tpi", "gpi"])
+@pytest.mark.parametrize("kernel", ["tpi", "gpi", "gpi_smem"])
 def test_max_iter_zero_returns_the_warm_state(kernel):
     """max_iter = 0: solve() skips its loop (admm.cpp:378) and reports solution = vnew/znew as they stand, iter = 0."""
     spec = wl.quadrotor(N=10)
@@ -344,7 +365,7 @@ def test_max_iter_zero_returns_the_warm_state(kernel):
     assert (g["iter"] == 0).all() and H.bits_equal(g["sol_x"], first["vnew"])
 
 
-@pytest.mark.parametrize("kernel", ["tpi", "gpi"])
+@pytest.mark.parametrize("kernel", ["tpi", "gpi", "gpi_smem"])
 @pytest.mark.parametrize("N", [2, 3, 5])
 def test_tiny_horizons(N, kernel):
     """N = 2 is the smallest horizon the reference can represent (one input column)."""

@@ -80,6 +80,7 @@ class Stats(C.Structure):
         ("instances_per_cta", C.c_int32), ("smem_bytes_per_cta", C.c_int32),
         ("ctas", C.c_int32), ("threads_per_cta", C.c_int32),
         ("gpi_instances", C.c_int64),
+        ("tmem_cols_per_cta", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 

@@ -385,6 +385,7 @@ int enqueue(tinympc_b200_solver *s, const tinympc_batch_t *io, cudaStream_t stre
         s->stats.instances_per_cta = d.out_instances_per_cta;
         s->stats.smem_bytes_per_cta = d.out_smem;
         s->stats.threads_per_cta = d.out_threads;
+        s->stats.tmem_cols_per_cta = d.out_tmem_cols;
     }
     if (Bt > 0) {
         d.family = TINYMPC_KERNEL_TPI;
@@ -404,6 +405,7 @@ int enqueue(tinympc_b200_solver *s, const tinympc_batch_t *io, cudaStream_t stre
             s->stats.instances_per_cta = d.out_instances_per_cta;
             s->stats.smem_bytes_per_cta = d.out_smem;
             s->stats.threads_per_cta = d.out_threads;
+            s->stats.tmem_cols_per_cta = 0;
         }
     }
     if (split) {

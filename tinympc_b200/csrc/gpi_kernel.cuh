@@ -41,6 +41,11 @@ struct GpiCfg {
     __host__ __device__ static constexpr size_t warp_elems(int N) {
         return (size_t)N * 32 * PVP * 2 + (size_t)(N - 1) * RU * 32 + GBUF;
     }
+    // TMEM variant (fp32): the dual pack and d live in tensor memory, CPK 32-bit columns per knot point in the
+    // lane of the owning thread; shared memory keeps the primal pack and the gather scratch
+    static constexpr int CPK = PVP + RU;
+    __host__ __device__ static constexpr size_t warp_elems_tm(int N) { return (size_t)N * 32 * PVP + GBUF; }
+    __host__ __device__ static constexpr int tm_cols(int N) { return N * CPK; }
 };
 
 template <typename T, int NX, int NU, int L>
@@ -88,6 +93,38 @@ __device__ __forceinline__ void stsv(unsigned a, const double (&v)[2]) {
     asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(a), "d"(v[0]), "d"(v[1]) : "memory");
 }
 
+// Tensor memory (TMEM, 128 lanes x 512 32-bit columns per SM) used as a per-thread scratchpad: warp w of a CTA owns
+// TMEM lanes [32*(w%4), +32), thread t of the warp lane 32*(w%4)+t.  `32x32b` moves n consecutive columns of the
+// thread's own lane to / from n registers.  Loads are asynchronous: tm_wait_ld() + tm_tie() before the first use.
+__device__ __forceinline__ void tm_ld(unsigned ta, float (&v)[1]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=f"(v[0]) : "r"(ta));
+}
+__device__ __forceinline__ void tm_ld(unsigned ta, float (&v)[2]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=f"(v[0]), "=f"(v[1]) : "r"(ta));
+}
+__device__ __forceinline__ void tm_ld(unsigned ta, float (&v)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(ta));
+}
+__device__ __forceinline__ void tm_st(unsigned ta, const float (&v)[1]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(ta), "f"(v[0]) : "memory");
+}
+__device__ __forceinline__ void tm_st(unsigned ta, const float (&v)[2]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(ta), "f"(v[0]), "f"(v[1]) : "memory");
+}
+__device__ __forceinline__ void tm_st(unsigned ta, const float (&v)[4]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(ta), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+}
+__device__ __forceinline__ void tm_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// makes every later use of v depend on an asm statement that is ordered after tm_wait_ld()
+__device__ __forceinline__ void tm_tie(float &v) { asm volatile("" : "+f"(v)); }
+// double overloads exist only so that the fp64 instantiations (never TMEM) parse
+__device__ __forceinline__ void tm_tie(double &) {}
+template <int n>
+__device__ __forceinline__ void tm_ld(unsigned, double (&)[n]) {}
+template <int n>
+__device__ __forceinline__ void tm_st(unsigned, const double (&)[n]) {}
+
 template <bool B>
 struct BoolTag {
     static constexpr bool value = B;
@@ -107,12 +144,13 @@ __device__ __forceinline__ T clamp_box(T v, T lo, T hi) {
 __device__ __forceinline__ float absmax(float m, float d) { return fmaxf(m, fabsf(d)); }
 __device__ __forceinline__ double absmax(double m, double d) { return fmax(m, fabs(d)); }
 
-template <typename T, int NX, int NU, int L, bool FAST, bool HET>
+template <typename T, int NX, int NU, int L, bool FAST, bool HET, bool TM>
 __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
     gpi_solve_kernel(const __grid_constant__ KParams<T, NX, NU> P, const T *__restrict__ gmat, unsigned long long *queue) {
     using Cfg = GpiCfg<NX, NU, L, (int)sizeof(T)>;
     constexpr int RX = Cfg::RX, RU = Cfg::RU, IPW = Cfg::IPW, W = Cfg::W, PVP = Cfg::PVP, NPV = Cfg::NPV;
-    constexpr int NXP = Cfg::NXP, NUP = Cfg::NUP;
+    constexpr int NXP = Cfg::NXP, NUP = Cfg::NUP, CPK = Cfg::CPK;
+    static_assert(!TM || sizeof(T) == 4, "the TMEM variant is fp32 only");
     constexpr bool EXACT = (RX * L == NX) && (RU * L == NU);  // no padding rows: predicates vanish
     constexpr unsigned ES = (unsigned)sizeof(T);
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -205,16 +243,32 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
         }
     };
     load_rows(stage);
+    // TMEM variant: warp 0 allocates all 512 columns (one CTA per SM); warps w and w+4 share a lane quarter and
+    // take the column ranges [0, N*CPK) and [N*CPK, 2*N*CPK)
+    unsigned tbase = 0;
+    __shared__ unsigned tmem_addr_slot;
+    if constexpr (TM) {
+        if (warp == 0) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"((unsigned)__cvta_generic_to_shared(&tmem_addr_slot)) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
     __syncthreads();  // staging area is reused as state below
+    if constexpr (TM) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        tbase = tmem_addr_slot + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)((warp >> 2) * N * CPK);
+    }
 
     // ---- shared-memory state of this warp ----
     //   PA[k][lane][PVP] : primal pack  (vnew rows of this lane, then znew rows)      16-byte vectors,
     //   PB[k][lane][PVP] : dual pack    (g rows, then y rows)                          conflict free
     //   D [k][b][lane]   : d
     //   GB[...]          : gather scratch (one vector of one instance per row)
-    const int warp_elems = (int)Cfg::warp_elems(N);
+    //   TMEM variant: PB and D live in tensor memory instead, columns [k*CPK, +PVP) and [k*CPK+PVP, +RU) of the thread's lane
+    const int warp_elems = TM ? (int)Cfg::warp_elems_tm(N) : (int)Cfg::warp_elems(N);
     T *wbase = reinterpret_cast<T *>(smem_raw) + (size_t)warp * warp_elems;
-    T *gPA = wbase, *gPB = gPA + N * 32 * PVP, *gD = gPB + N * 32 * PVP, *gGB = gD + (N - 1) * RU * 32;
+    T *gPA = wbase, *gPB = gPA + N * 32 * PVP, *gD = gPB + N * 32 * PVP, *gGB = TM ? gPA + N * 32 * PVP : gD + (N - 1) * RU * 32;
     const unsigned aPA = (unsigned)__cvta_generic_to_shared(gPA) + (unsigned)(lane * PVP) * ES;
     const unsigned aPB = (unsigned)__cvta_generic_to_shared(gPB) + (unsigned)(lane * PVP) * ES;
     const unsigned aD = (unsigned)__cvta_generic_to_shared(gD) + (unsigned)lane * ES;
@@ -237,6 +291,73 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
 #pragma unroll
             for (int e = 0; e < W; ++e) t[e] = v[c * W + e];
             stsv(base + (unsigned)k * KSTR + (unsigned)(c * W) * ES, t);
+        }
+    };
+    // dual pack / d accessors.  TMEM loads are asynchronous: `pb_ready` / `d_ready` must run before the first use.
+    auto load_pb = [&](int k, T (&v)[PVP]) {
+        if constexpr (TM) {
+#pragma unroll
+            for (int c = 0; c < NPV; ++c) {
+                T t[W];
+                tm_ld(tbase + (unsigned)(k * CPK + c * W), t);
+#pragma unroll
+                for (int e = 0; e < W; ++e) v[c * W + e] = t[e];
+            }
+        } else {
+            load_pack(aPB, k, v);
+        }
+    };
+    auto pb_ready = [&](T (&v)[PVP]) {
+        if constexpr (TM) {
+            tm_wait_ld();
+#pragma unroll
+            for (int e = 0; e < PVP; ++e) tm_tie(v[e]);
+        }
+    };
+    auto store_pb = [&](int k, const T (&v)[PVP]) {  // TMEM: warp-wide, unconditional
+        if constexpr (TM) {
+#pragma unroll
+            for (int c = 0; c < NPV; ++c) {
+                T t[W];
+#pragma unroll
+                for (int e = 0; e < W; ++e) t[e] = v[c * W + e];
+                tm_st(tbase + (unsigned)(k * CPK + c * W), t);
+            }
+        } else {
+            store_pack(aPB, k, v);
+        }
+    };
+    auto load_d = [&](int k, T (&d)[RU]) {
+        if constexpr (TM) {
+#pragma unroll
+            for (int b = 0; b < RU; ++b) {
+                T t[1];
+                tm_ld(tbase + (unsigned)(k * CPK + PVP + b), t);
+                d[b] = t[0];
+            }
+        } else {
+#pragma unroll
+            for (int b = 0; b < RU; ++b) d[b] = lds(aD + (unsigned)k * DSTR + (unsigned)(b * 32) * ES, T());
+        }
+    };
+    auto d_ready = [&](T (&d)[RU]) {
+        if constexpr (TM) {
+            tm_wait_ld();
+#pragma unroll
+            for (int b = 0; b < RU; ++b) tm_tie(d[b]);
+        }
+    };
+    auto store_d = [&](int k, const T (&d)[RU], const bool live) {
+        if constexpr (TM) {
+#pragma unroll
+            for (int b = 0; b < RU; ++b) {
+                T t[1] = {d[b]};
+                tm_st(tbase + (unsigned)(k * CPK + PVP + b), t);
+            }
+        } else {
+#pragma unroll
+            for (int b = 0; b < RU; ++b)
+                if (live && uv[b]) sts(aD + (unsigned)k * DSTR + (unsigned)(b * 32) * ES, d[b]);
         }
     };
     // all-gather inside the lane group through shared memory: every lane stores its R values, then reads the
@@ -317,7 +438,7 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
 #pragma unroll
         for (int b = 0; b < RU; ++b) ur[b] = (has_uref && uv[b]) ? __ldg(up + b) : T(0);
         load_pack(aPA, k, pa);
-        load_pack(aPB, k, pb);
+        load_pb(k, pb);
     };
     auto cost_eval = [&](const T (&xr)[RX], const T (&ur)[RU], const T (&pa)[PVP], const T (&pb)[PVP], T (&q)[RX], T (&r)[RU]) {
 #pragma unroll
@@ -335,10 +456,9 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
         for (int a = 0; a < RX; ++a) xo[a] = x0o[a];
         gather_x(xo, Xf);
         // one column: slack + dual update of this lane's rows, residual maxima; HASU = the column has inputs
-        auto column = [&](int k, const bool HASU, const T (&u)[RU], const T (&vprev)[PVP]) {  // always inlined with a literal HASU
-            T pa[PVP], pb[PVP], na[PVP], nb[PVP];
+        auto column = [&](int k, const bool HASU, const T (&u)[RU], const T (&vprev)[PVP], const T (&pb)[PVP]) {  // always inlined with a literal HASU
+            T pa[PVP], na[PVP], nb[PVP];
             load_pack(aPA, k, pa);
-            load_pack(aPB, k, pb);
 #pragma unroll
             for (int e = 0; e < PVP; ++e) {
                 na[e] = pa[e];
@@ -384,9 +504,10 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
                     rdu = absmax(rdu, zo - z);
                 }
             }
+            if constexpr (TM) store_pb(k, nb);  // (a slot that is not busy holds no live state)
             if (busy) {
                 store_pack(aPA, k, na);
-                store_pack(aPB, k, nb);
+                if constexpr (!TM) store_pb(k, nb);
                 if constexpr (SLOW) {
                     // work->v / work->z of this iteration = the primal pack as it was before this column's update
                     // (kept in pack layout in global scratch: one 16-byte store; transposed out only if the solve converges)
@@ -423,27 +544,31 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
             }
         };
         for (int k = 0; k < N - 1; ++k) {
-            T u[RU], Uf[NU], t1[RX + RU], bu[RX], vprev[PVP];
+            T u[RU], Uf[NU], t1[RX + RU], bu[RX], vprev[PVP], pbk[PVP], dk[RU];
             load_vprev(k, vprev);
+            load_pb(k, pbk);
+            load_d(k, dk);
             dots<FAST>(mS1f, Xf, t1);  // [A x_k ; Kinf x_k]
+            d_ready(dk);
+            pb_ready(pbk);
 #pragma unroll
-            for (int b = 0; b < RU; ++b) {  // u_k = -(Kinf x_k) - d_k
-                const T d = lds(aD + (unsigned)k * DSTR + (unsigned)(b * 32) * ES, T());
-                u[b] = (-t1[RX + b]) - d;
-            }
+            for (int b = 0; b < RU; ++b) u[b] = (-t1[RX + b]) - dk[b];  // u_k = -(Kinf x_k) - d_k
             gather_u(u, Uf);
-            column(k, true, u, vprev);
+            column(k, true, u, vprev, pbk);
             dots<FAST>(mB, Uf, bu);
 #pragma unroll
             for (int a = 0; a < RX; ++a) xo[a] = (t1[a] + bu[a]) + vf[a];  // x_{k+1} = (A x_k + B u_k) + f
             gather_x(xo, Xf);
         }
         {
-            T udummy[RU], vprev[PVP];
+            T udummy[RU], vprev[PVP], pbk[PVP];
 #pragma unroll
             for (int b = 0; b < RU; ++b) udummy[b] = T(0);
             load_vprev(N - 1, vprev);
-            column(N - 1, false, udummy, vprev);
+            load_pb(N - 1, pbk);
+            pb_ready(pbk);
+            column(N - 1, false, udummy, vprev, pbk);
+            if constexpr (TM) tm_wait_st();  // the dual packs are read back by the next backward pass / the write-back
         }
     };
 
@@ -460,10 +585,47 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
             for (int e = lane; e < N * VPK; e += 32) {
                 const int k = e / VPK, w = e - k * VPK;
                 a4[k * ROW4 + s * VPK + w] = z4;
-                b4[k * ROW4 + s * VPK + w] = z4;
+                if constexpr (!TM) b4[k * ROW4 + s * VPK + w] = z4;
             }
         }
         __syncwarp();
+        if constexpr (TM) {
+            // the dual packs live in the lanes' own TMEM columns and TMEM stores are warp-wide: read-modify-write every
+            // knot point, replacing the values of slot s's lanes by zeros (cold) or the caller's g / y rows (warm start);
+            // the global loads of UNR knot points are issued together, ahead of the dependent TMEM traffic
+            const int64_t ox = ib * (int64_t)N * NX, ou = ib * (int64_t)(N - 1) * NU;
+            const bool mine = slot == s;
+            constexpr int UNR = 5;
+            for (int k0 = 0; k0 < N; k0 += UNR) {
+                T nv[UNR][PVP];
+#pragma unroll
+                for (int t = 0; t < UNR; ++t) {
+                    const int k = k0 + t;
+#pragma unroll
+                    for (int e = 0; e < PVP; ++e) nv[t][e] = T(0);
+#pragma unroll
+                    for (int a = 0; a < RX; ++a)
+                        nv[t][a] = (!cold && mine && k < N && xv[a] && P.s_g) ? P.s_g[ox + (int64_t)k * NX + l * RX + a] : T(0);
+#pragma unroll
+                    for (int b = 0; b < RU; ++b)
+                        nv[t][RX + b] = (!cold && mine && k < N - 1 && uv[b] && P.s_y) ? P.s_y[ou + (int64_t)k * NU + l * RU + b] : T(0);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int t = 0; t < UNR; ++t) {
+                    const int k = k0 + t;
+                    if (k < N) {  // warp-uniform
+                        T old[PVP];
+                        load_pb(k, old);
+                        pb_ready(old);
+#pragma unroll
+                        for (int e = 0; e < PVP; ++e) old[e] = mine ? nv[t][e] : old[e];
+                        store_pb(k, old);
+                    }
+                }
+            }
+            tm_wait_st();
+        }
         if (!cold) {
             // warm start: the instance's vnew/g/znew/y blocks are contiguous in global memory; loads are batched four
             // deep before the dependent shared-memory stores (one warp cannot hide a load-use pair per iteration)
@@ -476,7 +638,7 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
                     const int e = e0 + 32 * t;
                     const bool ok = e < N * NX;
                     va[t] = (ok && P.s_vnew) ? P.s_vnew[ox + e] : T(0);
-                    vb[t] = (ok && P.s_g) ? P.s_g[ox + e] : T(0);
+                    vb[t] = (!TM && ok && P.s_g) ? P.s_g[ox + e] : T(0);
                 }
 #pragma unroll
                 for (int t = 0; t < UNR; ++t) {
@@ -485,7 +647,7 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
                         const int k = e / NX, i = e - k * NX;
                         const int w = idx_x(s, k, i);
                         gPA[w] = va[t];
-                        gPB[w] = vb[t];
+                        if constexpr (!TM) gPB[w] = vb[t];
                     }
                 }
             }
@@ -496,7 +658,7 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
                     const int e = e0 + 32 * t;
                     const bool ok = e < (N - 1) * NU;
                     va[t] = (ok && P.s_znew) ? P.s_znew[ou + e] : T(0);
-                    vb[t] = (ok && P.s_y) ? P.s_y[ou + e] : T(0);
+                    vb[t] = (!TM && ok && P.s_y) ? P.s_y[ou + e] : T(0);
                 }
 #pragma unroll
                 for (int t = 0; t < UNR; ++t) {
@@ -505,7 +667,7 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
                         const int k = e / NU, j = e - k * NU;
                         const int w = idx_u(s, k, j);
                         gPA[w] = va[t];
-                        gPB[w] = vb[t];
+                        if constexpr (!TM) gPB[w] = vb[t];
                     }
                 }
             }
@@ -631,7 +793,8 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
             const T v = gPA[w];
             if (P.sol_x) P.sol_x[ox + e] = v;
             if (P.s_vnew) P.s_vnew[ox + e] = v;
-            if (P.s_g) P.s_g[ox + e] = gPB[w];
+            if constexpr (!TM)
+                if (P.s_g) P.s_g[ox + e] = gPB[w];
             // work->v: previous vnew if the solve converged (staged in the scratch during the last forward pass; unchanged
             // if that was the first iteration of a warm start), else = vnew (admm.cpp:445); untouched when no iteration
             // ran on a warm start
@@ -645,10 +808,32 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
             const T z = gPA[w];
             if (P.sol_u) P.sol_u[ou + e] = z;
             if (P.s_znew) P.s_znew[ou + e] = z;
-            if (P.s_y) P.s_y[ou + e] = gPB[w];
+            if constexpr (!TM)
+                if (P.s_y) P.s_y[ou + e] = gPB[w];
             if (P.s_z && !s_solved && s_it > 0) P.s_z[ou + e] = z;
             else if (P.s_z && s_solved && !(s_it == 1 && !cold)) P.s_z[ou + e] = P.gpi_vscratch[((ib * N + k) * L + j / RU) * PVP + RX + (j % RU)];
             else if (P.s_z && cold && s_it == 0) P.s_z[ou + e] = T(0);
+        }
+        if constexpr (TM) {
+            if (P.s_g || P.s_y) {  // work->g / work->y from the lanes' own TMEM columns
+                __syncwarp();
+                for (int k = 0; k < N; ++k) {
+                    T v[PVP];
+                    load_pb(k, v);
+                    pb_ready(v);
+                    if (slot == s) {
+#pragma unroll
+                        for (int a = 0; a < RX; ++a)
+                            if (xv[a] && P.s_g) P.s_g[ox + (int64_t)k * NX + l * RX + a] = v[a];
+                        if (k < N - 1) {
+#pragma unroll
+                            for (int b = 0; b < RU; ++b)
+                                if (uv[b] && P.s_y) P.s_y[ou + (int64_t)k * NU + l * RU + b] = v[RX + b];
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
         }
         // work->u.col(0): one rollout step from d_0 (every lane computes, the lanes of slot s store)
         if (P.u0) {
@@ -657,11 +842,13 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
 #pragma unroll
             for (int a = 0; a < RX; ++a) xo0[a] = x0o[a];
             gather_x(xo0, Xf0);
+            T d0[RU];
+            load_d(0, d0);
             dots<FAST>(mS1f, Xf0, t10);
+            d_ready(d0);
 #pragma unroll
             for (int b = 0; b < RU; ++b) {
-                const T d = lds(aD + (unsigned)(b * 32) * ES, T());
-                T u0v = (-t10[RX + b]) - d;
+                T u0v = (-t10[RX + b]) - d0[b];
                 if (s_it == 0) u0v = (!cold && P.s_u) ? P.s_u[ou + l * RU + b] : T(0);
                 if (slot == s && uv[b]) P.u0[ib * NU + l * RU + b] = u0v;
             }
@@ -683,12 +870,13 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
 #pragma unroll
                 for (int a = 0; a < RX; ++a) na[a] = xo[a];
                 if (k < N - 1) {
-                    T u[RU], Uf[NU], t1[RX + RU], bu[RX];
+                    T u[RU], Uf[NU], t1[RX + RU], bu[RX], dk[RU];
+                    load_d(k, dk);
                     dots<FAST>(mS1f, Xf, t1);
+                    d_ready(dk);
 #pragma unroll
                     for (int b = 0; b < RU; ++b) {
-                        const T d = lds(aD + (unsigned)k * DSTR + (unsigned)(b * 32) * ES, T());
-                        u[b] = (-t1[RX + b]) - d;
+                        u[b] = (-t1[RX + b]) - dk[b];
                         na[RX + b] = u[b];
                     }
                     gather_u(u, Uf);
@@ -754,7 +942,8 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
         {
             T pa[PVP], pb[PVP];
             load_pack(aPA, N - 1, pa);
-            load_pack(aPB, N - 1, pb);
+            load_pb(N - 1, pb);
+            pb_ready(pb);
 #pragma unroll
             for (int a = 0; a < RX; ++a) po[a] = nmac<FAST>(pterm[a], rho_(), pa[a] - pb[a]);
         }
@@ -765,6 +954,7 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
         {
             T xr[RX], ur[RU], pa[PVP], pb[PVP];
             cost_load(N - 2, xp, up, xr, ur, pa, pb);
+            pb_ready(pb);
             cost_eval(xr, ur, pa, pb, q, r);
         }
         gather_u(r, Rf);
@@ -789,16 +979,16 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
             for (int a = 0; a < RX; ++a) po[a] = ((q[a] + acc1[a]) - kr[a]) + vAPf[a];
             if (MORE) gather_x(po, Pf);  // p_0 itself is never used (the forward pass starts from x_0)
             dots<FAST>(mQuu, Sf, dq);
-#pragma unroll
-            for (int b = 0; b < RU; ++b)
-                if (busy && uv[b]) sts(aD + (unsigned)k * DSTR + (unsigned)(b * 32) * ES, dq[b]);
+            store_d(k, dq, busy);
             if (MORE) {
+                pb_ready(pb_n);
                 cost_eval(xr_n, ur_n, pa_n, pb_n, q, r);
                 gather_u(r, Rf);
             }
         };
         for (int k = N - 2; k >= 1; --k) bwd_step(k, true);
         bwd_step(0, false);
+        if constexpr (TM) tm_wait_st();  // d is read back by the forward pass
         __syncwarp();
 
         T rpx = T(0), rdx = T(0), rpu = T(0), rdu = T(0);
@@ -823,6 +1013,11 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
         }
         } while (!__any_sync(0xffffffffu, busy && (solved || it >= P.max_iter)));
     }
+    if constexpr (TM) {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_addr_slot) : "memory");
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -831,16 +1026,29 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
 struct GpiPlan {
     int L = 0, warps = 0;
     size_t smem = 0;
+    bool tm = false;  // dual packs + d in tensor memory (fp32)
 };
 
-template <typename T, int NX, int NU, int L>
+// TINYMPC_GPI_TMEM=0 keeps everything in shared memory (A/B switch for measurements)
+inline bool gpi_allow_tm() {
+    const char *e = std::getenv("TINYMPC_GPI_TMEM");
+    return !(e && e[0] == '0');
+}
+
+template <typename T, int NX, int NU, int L, bool TM>
 inline void gpi_consider(int N, int max_smem, GpiPlan &best) {
-    if constexpr (gpi_feasible<T, NX, NU, L>()) {
+    if constexpr (gpi_feasible<T, NX, NU, L>() && (!TM || sizeof(T) == 4)) {
         using Cfg = GpiCfg<NX, NU, L, (int)sizeof(T)>;
-        const size_t per_warp = Cfg::warp_elems(N) * sizeof(T);
+        const size_t per_warp = (TM ? Cfg::warp_elems_tm(N) : Cfg::warp_elems(N)) * sizeof(T);
         // the TMA staging area aliases the start of the state region: the allocation is at least as large as the blob
         const size_t blob = ((size_t)(3 * NX * NX + 2 * NX * NU + NU * NU + 4 * NX + 2 * NU) * sizeof(T) + 15) / 16 * 16 + 64;
         int w = (int)std::min<size_t>(GPI_MAX_WARPS, (size_t)max_smem / per_warp);
+        if (TM) {
+            // every TMEM lane quarter is shared by the warps w, w+4, ...: 512 columns / (N*CPK columns per warp)
+            const int cols = Cfg::tm_cols(N);
+            if (cols > 512) return;
+            w = std::min(w, 4 * (512 / cols));
+        }
         if (w < 1 || blob > (size_t)max_smem) return;
         // score: instances resident per SM, then fewer lanes per instance (less shuffle traffic)
         const int inst = w * Cfg::IPW, binst = best.warps * (best.L ? 32 / best.L : 0);
@@ -849,6 +1057,7 @@ inline void gpi_consider(int N, int max_smem, GpiPlan &best) {
             best.L = L;
             best.warps = w;
             best.smem = std::max(per_warp * (size_t)w, blob);
+            best.tm = TM;
         }
     }
 }
@@ -856,9 +1065,14 @@ inline void gpi_consider(int N, int max_smem, GpiPlan &best) {
 template <typename T, int NX, int NU>
 inline GpiPlan gpi_plan(int N, int max_smem) {
     GpiPlan p;
-    gpi_consider<T, NX, NU, 4>(N, max_smem, p);
-    gpi_consider<T, NX, NU, 8>(N, max_smem, p);
-    gpi_consider<T, NX, NU, 16>(N, max_smem, p);
+    gpi_consider<T, NX, NU, 4, false>(N, max_smem, p);
+    gpi_consider<T, NX, NU, 8, false>(N, max_smem, p);
+    gpi_consider<T, NX, NU, 16, false>(N, max_smem, p);
+    if (gpi_allow_tm()) {  // taken only when it holds more instances per SM
+        gpi_consider<T, NX, NU, 4, true>(N, max_smem, p);
+        gpi_consider<T, NX, NU, 8, true>(N, max_smem, p);
+        gpi_consider<T, NX, NU, 16, true>(N, max_smem, p);
+    }
     return p;
 }
 
@@ -867,10 +1081,10 @@ inline int gpi_fit_T(int N, int max_smem) {
     return (int)gpi_plan<T, NX, NU>(N, max_smem).smem;
 }
 
-template <typename T, int NX, int NU, int L, bool FAST, bool HET>
+template <typename T, int NX, int NU, int L, bool FAST, bool HET, bool TM>
 int launch_gpi_L(LaunchDesc *d, const GpiPlan &plan, const KParams<T, NX, NU> &P, const T *gmat) {
-    if constexpr (gpi_feasible<T, NX, NU, L>()) {
-        auto kern = gpi_solve_kernel<T, NX, NU, L, FAST, HET>;
+    if constexpr (gpi_feasible<T, NX, NU, L>() && (!TM || sizeof(T) == 4)) {
+        auto kern = gpi_solve_kernel<T, NX, NU, L, FAST, HET, TM>;
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem) != cudaSuccess)
             return TINYMPC_ERR_CUDA;
         const int64_t ngroups = (d->io.B + (32 / L) - 1) / (32 / L);
@@ -882,6 +1096,7 @@ int launch_gpi_L(LaunchDesc *d, const GpiPlan &plan, const KParams<T, NX, NU> &P
         d->out_smem = (int)plan.smem;
         d->out_lanes_per_instance = L;
         d->out_instances_per_cta = plan.warps * (32 / L);
+        d->out_tmem_cols = TM ? 512 : 0;
         return cudaGetLastError() == cudaSuccess ? TINYMPC_OK : TINYMPC_ERR_CUDA;
     } else {
         return TINYMPC_ERR_UNSUPPORTED;

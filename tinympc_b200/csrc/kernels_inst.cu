@@ -105,6 +105,7 @@ int launch_tpi(LaunchDesc *d) {
     d->out_smem = 0;
     d->out_lanes_per_instance = 1;
     d->out_instances_per_cta = threads;
+    d->out_tmem_cols = 0;
     return cudaGetLastError() == cudaSuccess ? TINYMPC_OK : TINYMPC_ERR_CUDA;
 }
 
@@ -116,14 +117,16 @@ int launch_gpi(LaunchDesc *d) {
     KParams<T, NX, NU> P;
     fill_params<T>(P, *d);
     const T *gmat = (const T *)d->gmat;
-    if (d->io.models) {  // heterogeneous batch: per-instance model blobs
-        if (plan.L == 4) return launch_gpi_L<T, NX, NU, 4, FAST, true>(d, plan, P, gmat);
-        if (plan.L == 8) return launch_gpi_L<T, NX, NU, 8, FAST, true>(d, plan, P, gmat);
-        return launch_gpi_L<T, NX, NU, 16, FAST, true>(d, plan, P, gmat);
-    }
-    if (plan.L == 4) return launch_gpi_L<T, NX, NU, 4, FAST, false>(d, plan, P, gmat);
-    if (plan.L == 8) return launch_gpi_L<T, NX, NU, 8, FAST, false>(d, plan, P, gmat);
-    return launch_gpi_L<T, NX, NU, 16, FAST, false>(d, plan, P, gmat);
+    const bool het = d->io.models != nullptr;  // heterogeneous batch: per-instance model blobs
+#define TM_GPI_CASE(LL, HH, TT) \
+    if (plan.L == LL && het == HH && plan.tm == TT) return launch_gpi_L<T, NX, NU, LL, FAST, HH, TT>(d, plan, P, gmat);
+#define TM_GPI_L(LL) TM_GPI_CASE(LL, false, false) TM_GPI_CASE(LL, true, false) TM_GPI_CASE(LL, false, true) TM_GPI_CASE(LL, true, true)
+    TM_GPI_L(4)
+    TM_GPI_L(8)
+    TM_GPI_L(16)
+#undef TM_GPI_L
+#undef TM_GPI_CASE
+    return TINYMPC_ERR_UNSUPPORTED;
 }
 #endif
 

@@ -43,7 +43,7 @@ struct LaunchDesc {
     int max_smem_optin;
 
     // filled by the launcher
-    int out_threads, out_ctas, out_smem, out_lanes_per_instance, out_instances_per_cta;
+    int out_threads, out_ctas, out_smem, out_lanes_per_instance, out_instances_per_cta, out_tmem_cols;
 };
 
 // per-(nx,nu) entry: returns 0 on success, TINYMPC_ERR_UNSUPPORTED when (dtype,family,...) is not compiled

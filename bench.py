@@ -315,7 +315,8 @@ def main():
         "config": {"workload": WORKLOAD, "mode": args.mode, "kernel": {1: "tpi", 2: "gpi", 3: "hybrid(gpi+tpi co-resident)"}[st["kernel_family"]],
                    "l2": "flushed (256 MiB write) between timed steps", "parallelism": f"batch-sharded x{world}, no data-path collective",
                    "lanes_per_instance": st["lanes_per_instance"], "ctas": st["ctas"], "threads_per_cta": st["threads_per_cta"],
-                   "smem_bytes_per_cta": st["smem_bytes_per_cta"], "gpi_instances": st["gpi_instances"]},
+                   "smem_bytes_per_cta": st["smem_bytes_per_cta"], "tmem_cols_per_cta": st["tmem_cols_per_cta"],
+                   "instances_per_cta": st["instances_per_cta"], "gpi_instances": st["gpi_instances"]},
         "admm_iters_per_s_per_gpu": red["iters"] / world / (red["ms"] * 1e-3),
         "solved_fraction": red["solved"] / red["instances"],
         "residual_max": red["res_max"],

@@ -193,11 +193,14 @@ int resolve_family(const tinympc_b200_solver *s, const Features &ft, int *smem_o
     if (s->family == TINYMPC_KERNEL_TPI) return TINYMPC_KERNEL_TPI;
     if (s->family == TINYMPC_KERNEL_HYBRID) return gpi_ok ? TINYMPC_KERNEL_HYBRID : -1;
     if (!gpi_ok) return TINYMPC_KERNEL_TPI;
-    // AUTO: GPI unless shared memory leaves it fewer than one warp per scheduler (long horizons / wide states) AND the
-    // batch is large enough to fill the GPU with one thread per instance (profiles/r01_sweep_1gpu.md).  HYBRID is opt-in.
+    // AUTO: GPI unless on-chip memory (shared + tensor memory) holds fewer than 32 instances per SM (long horizons with
+    // wide inputs) AND the batch is large enough to fill the GPU with one thread per instance.  Measured on B200
+    // (profiles/r01_sweep_1gpu.md, B = 131 072, N = 100): at 16 instances/SM TPI wins by 10-35 % for every shape except
+    // (16,8), where its register footprint costs more than the low GPI occupancy; at >= 32 instances/SM GPI always wins.
     const int plan = s->dim->gpi_instances_per_cta ? s->dim->gpi_instances_per_cta(s->dtype, s->N, s->max_smem_optin) : 0;
-    const int warps = plan >> 16;
-    if (warps > 0 && warps < 4 && B >= (int64_t)s->sm_count * 384) return TINYMPC_KERNEL_TPI;
+    const int ipc = plan & 0xffff;
+    const bool tpi_heavy = s->nx >= 16 && s->nu >= 8;
+    if (ipc > 0 && ipc < 32 && !tpi_heavy && B >= (int64_t)s->sm_count * 384) return TINYMPC_KERNEL_TPI;
     return TINYMPC_KERNEL_GPI;
 }
 

@@ -62,7 +62,7 @@ def row(name, spec, dt, inst, B, kernel, kname, mode, mname, per_inst_ref):
     es = np.dtype(dt).itemsize
     gbs = B * bytes_inst(spec.nx, spec.nu, spec.N, es, per_inst_ref) / (ms * 1e-3) / 1e9
     tf = iters * flops_iter(spec.nx, spec.nu, spec.N) / (ms * 1e-3) / 1e12
-    fam = {1: "tpi", 2: f"gpi L={st['lanes_per_instance']}", 3: "hybrid"}[st["kernel_family"]]
+    fam = {1: "tpi", 2: f"gpi L={st['lanes_per_instance']} {st['instances_per_cta']}/SM" + (" tmem" if st["tmem_cols_per_cta"] else ""), 3: "hybrid"}[st["kernel_family"]]
     print(f"| {name} | {spec.nx} | {spec.nu} | {spec.N} | {B} | {np.dtype(dt).name} | {fam} | {mname} | {ms:.3f} | {B / ms * 1e3:.3e} | "
           f"{iters / ms * 1e3:.3e} | {solved / B:.2f} | {gbs:.1f} | {gbs / HBM:.5f} | {tf:.2f} |", flush=True)
 
@@ -87,3 +87,5 @@ for nx in (4, 8, 12, 16):
             spec.settings.max_iter = 50
             inst = wl.random_instances(a.B, nx, N, seed=2)
             row("C5 LTI fixed-work", spec, np.float32, inst, a.B, abi.KERNEL_AUTO, "auto", S, "strict", False)
+            if N == 100 and nu != 2:  # the AUTO rule's evidence: both families on the long horizons
+                row("C5 (forced tpi)", spec, np.float32, inst, a.B, abi.KERNEL_TPI, "tpi", S, "strict", False)

@@ -1,18 +1,20 @@
 // gpi_kernel.cuh — lane-group-per-instance (GPI) batched ADMM solve with the whole per-instance state
-// resident in shared memory.  This is the kernel BASELINE.json's north_star describes.
+// resident on chip.  This is the kernel BASELINE.json's north_star describes.
 //
 //   * L lanes (4, 8 or 16) own one MPC instance, 32/L instances per warp; lane l owns the state rows
 //     [l*RX, (l+1)*RX) and the input rows [l*RU, (l+1)*RU)  (RX = ceil(nx/L), RU = ceil(nu/L)) of every vector.
 //   * the rows of Kinf / Quu_inv / AmBKt / A / B that a lane needs are loaded ONCE into registers (staged
 //     through shared memory by a TMA bulk copy, cp.async.bulk), the p / x recursions run in registers, each
 //     mat-vec is RX (or RU) independent ascending-k dot products per lane (bit-identical to the pinned
-//     oracle in STRICT mode), and the freshly computed vector is all-gathered inside the lane group with
-//     warp shuffles;
-//   * the N-indexed state (vnew, g, znew, y, d) lives in shared memory for the whole solve, laid out
-//     [k][row slot][lane] so that every access of a warp is bank-conflict free; only the final
-//     trajectories / residuals are written back, through a coalescing transpose;
-//   * the kernel is persistent: one CTA per SM, every warp pulls the next group of 32/L instances from
-//     a global atomic counter until the batch is exhausted.
+//     oracle in STRICT mode), and the freshly computed vector is all-gathered inside the lane group through
+//     a small shared-memory buffer (STS + 16-byte broadcast LDS);
+//   * the N-indexed state lives on chip for the whole solve: the primal pack (vnew rows, znew rows) as one
+//     16-byte vector per lane and knot point in shared memory; the dual pack (g rows, y rows) and d either next
+//     to it in shared memory, or (TM = true, fp32) in TENSOR MEMORY — 5 of the thread's own 32-bit TMEM columns
+//     per knot point, tcgen05.ld/st.32x32b — which halves the shared-memory footprint and doubles the instances
+//     (= warps) resident per SM; only the final trajectories / residuals are written back;
+//   * the kernel is persistent: one CTA per SM; every lane group ("slot") pulls its next instance from a
+//     global atomic counter as soon as its current one terminates (per-instance termination, admm.cpp:310-328).
 // Reference semantics: tiny_solve -> solve (admm.cpp:331-455); per-iteration order as in SURVEY A.2.
 // Scope: box constraints (admm.cpp:85-98).  Cones / hyperplanes run on the TPI kernel.
 #pragma once

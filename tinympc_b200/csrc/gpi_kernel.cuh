@@ -1067,13 +1067,21 @@ inline void gpi_consider(int N, int max_smem, GpiPlan &best) {
 template <typename T, int NX, int NU>
 inline GpiPlan gpi_plan(int N, int max_smem) {
     GpiPlan p;
+    // L = 16 is only ever needed in fp64 (two registers per matrix entry: L = 4 / 8 exceed the register ceiling from
+    // nx = 12 on); for fp32 L = 8 covers every (nx, nu) pair of TM_DIMS, so the fp32 L = 16 kernels are compiled only
+    // with -DTM_GPI_L16 (wider states) to keep the build short
+    constexpr bool L16 = sizeof(T) == 8
+#ifdef TM_GPI_L16
+                         || true
+#endif
+        ;
     gpi_consider<T, NX, NU, 4, false>(N, max_smem, p);
     gpi_consider<T, NX, NU, 8, false>(N, max_smem, p);
-    gpi_consider<T, NX, NU, 16, false>(N, max_smem, p);
+    if constexpr (L16) gpi_consider<T, NX, NU, 16, false>(N, max_smem, p);
     if (gpi_allow_tm()) {  // taken only when it holds more instances per SM
         gpi_consider<T, NX, NU, 4, true>(N, max_smem, p);
         gpi_consider<T, NX, NU, 8, true>(N, max_smem, p);
-        gpi_consider<T, NX, NU, 16, true>(N, max_smem, p);
+        if constexpr (L16) gpi_consider<T, NX, NU, 16, true>(N, max_smem, p);
     }
     return p;
 }

@@ -123,7 +123,14 @@ int launch_gpi(LaunchDesc *d) {
 #define TM_GPI_L(LL) TM_GPI_CASE(LL, false, false) TM_GPI_CASE(LL, true, false) TM_GPI_CASE(LL, false, true) TM_GPI_CASE(LL, true, true)
     TM_GPI_L(4)
     TM_GPI_L(8)
+#ifdef TM_GPI_L16
     TM_GPI_L(16)
+#else
+    if constexpr (sizeof(T) == 8) {  // fp64 needs L = 16 from nx = 12 on (see gpi_plan)
+        TM_GPI_CASE(16, false, false)
+        TM_GPI_CASE(16, true, false)
+    }
+#endif
 #undef TM_GPI_L
 #undef TM_GPI_CASE
     return TINYMPC_ERR_UNSUPPORTED;

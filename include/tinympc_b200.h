@@ -219,6 +219,17 @@ int tinympc_b200_precompute_cache_batch(int32_t dtype, int32_t nx, int32_t nu, i
                                         const void *f, const void *Qdiag, const void *Rdiag, const void *rho,
                                         void *models_out, int32_t nthreads);
 
+/*
+ * The same computation ON THE DEVICE of handle `h` (one warp per instance, precompute_kernel.cuh), for batches whose
+ * models change often (per-instance re-linearisation): all pointers are device pointers of the handle's dtype, layouts
+ * as above; nx, nu are the handle's.  Asynchronous on `stream`.  The blobs are bit-identical to the host routine's.
+ * sweeps_out (optional, [B]): Riccati sweeps used per instance, -1 where a matrix was singular (that blob's cache is
+ * then undefined).  models_out can be passed straight to tinympc_b200_solve as tinympc_batch_t.models.
+ */
+int tinympc_b200_precompute_cache_batch_device(tinympc_b200_solver_t *h, int64_t B, const void *A, const void *Bm, const void *f,
+                                               const void *Qdiag, const void *Rdiag, const void *rho, void *models_out,
+                                               int32_t *sweeps_out, void *stream);
+
 /* tiny_setup (tiny_api.hpp:10-12) minus the precompute: uploads the problem to `device`. */
 int tinympc_b200_create(const tinympc_problem_t *problem, int32_t device, tinympc_b200_solver_t **out);
 int tinympc_b200_destroy(tinympc_b200_solver_t *s);

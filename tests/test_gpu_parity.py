@@ -419,3 +419,27 @@ def test_heterogeneous_models_per_instance(dt):
     with pytest.raises(TinyMPCError) as e:
         s2.solve(inst["x0"], inst["Xref"], None, cold_start=True, models=blobs)
     assert e.value.code == abi.ERR_UNSUPPORTED
+
+
+@pytest.mark.parametrize("dims", [(4, 1), (12, 4), (16, 8)])
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_device_precompute_bit_identical_to_host_precompute(dt, dims):
+    """the batched cache precompute on the device (one warp per model) produces exactly the blobs of the
+    host routine (which restates tiny_api.cpp:117-118,307-381), including the number of Riccati sweeps' effect."""
+    import torch
+    from tinympc_b200.solver import setup_models
+
+    nx, nu = dims
+    Bn = 67
+    specs = [wl.random_lti(nx, nu, 10, seed=100 + i) for i in range(Bn)]
+    rhos = np.array([0.5 + 0.25 * (i % 7) for i in range(Bn)])
+    args = (np.stack([s.A for s in specs]), np.stack([s.B for s in specs]), np.stack([s.f for s in specs]),
+            np.stack([s.Qdiag for s in specs]), np.stack([s.Rdiag for s in specs]), rhos)
+    host = setup_models(nx, nu, *args, dtype=dt)
+    prob = setup_problem(specs[0], dt)
+    solver = _mk_solver(prob, specs[0].settings, "auto")
+    dev, sweeps = solver.setup_models_device(*args, want_sweeps=True)
+    torch.cuda.synchronize()
+    assert H.bits_equal(dev.cpu().numpy(), host)
+    sw = sweeps.cpu().numpy()
+    assert (sw > 1).all() and (sw <= 1000).all() and len(set(sw.tolist())) > 1

@@ -90,6 +90,7 @@ EXPORTS = [
     "tinympc_b200_precompute_cache",
     "tinympc_b200_model_blob_elems",
     "tinympc_b200_precompute_cache_batch",
+    "tinympc_b200_precompute_cache_batch_device",
     "tinympc_b200_create",
     "tinympc_b200_destroy",
     "tinympc_b200_update_settings",

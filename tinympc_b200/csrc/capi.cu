@@ -531,6 +531,20 @@ int tinympc_b200_precompute_cache_batch(int32_t dtype, int32_t nx, int32_t nu, i
     return fail(TINYMPC_ERR_ARG, "bad dtype");
 }
 
+int tinympc_b200_precompute_cache_batch_device(tinympc_b200_solver_t *s, int64_t B, const void *A, const void *Bm, const void *f,
+                                               const void *Qdiag, const void *Rdiag, const void *rho, void *models_out,
+                                               int32_t *sweeps_out, void *stream) {
+    if (!s) return fail(TINYMPC_ERR_ARG, "null handle");
+    if (!A || !Bm || !f || !Qdiag || !Rdiag || !rho || !models_out || B < 0) return fail(TINYMPC_ERR_ARG, "null pointer or bad size");
+    if (B == 0) return TINYMPC_OK;
+    CUDA_TRY(cudaSetDevice(s->device));
+    const int rc = s->dim->precompute_batch(s->dtype, B, A, Bm, f, Qdiag, Rdiag, rho, models_out, sweeps_out, s->sm_count,
+                                            (cudaStream_t)stream);
+    if (rc == TINYMPC_ERR_CUDA) return fail(rc, std::string("precompute kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+    if (rc) return fail(rc, "precompute kernel unavailable for this dtype");
+    return TINYMPC_OK;
+}
+
 int tinympc_b200_create(const tinympc_problem_t *p, int32_t device, tinympc_b200_solver_t **out) {
     if (!p || !out) return fail(TINYMPC_ERR_ARG, "null argument");
     *out = nullptr;

@@ -10,6 +10,7 @@
 #ifdef TM_WITH_GPI
 #include "gpi_kernel.cuh"
 #endif
+#include "precompute_kernel.cuh"
 
 #ifndef TM_NX
 #error "compile with -DTM_NX=<nx> -DTM_NU=<nu>"
@@ -182,12 +183,21 @@ int gpi_ipc(int dtype, int N, int max_smem_optin) {
     return 0;
 }
 
+int precompute_batch(int dtype, int64_t B, const void *A, const void *Bm, const void *f, const void *Qdiag, const void *Rdiag,
+                     const void *rho, void *models_out, int32_t *sweeps_out, int sm_count, cudaStream_t stream) {
+    if (dtype == TINYMPC_F32)
+        return launch_precompute_T<float, TM_NX, TM_NU>(B, A, Bm, f, Qdiag, Rdiag, rho, models_out, sweeps_out, sm_count, stream);
+    if (dtype == TINYMPC_F64)
+        return launch_precompute_T<double, TM_NX, TM_NU>(B, A, Bm, f, Qdiag, Rdiag, rho, models_out, sweeps_out, sm_count, stream);
+    return TINYMPC_ERR_ARG;
+}
+
 }  // namespace
 }  // namespace tmpc
 
 #define TM_CAT2(a, b, c) a##b##_##c
 #define TM_CAT(a, b, c) TM_CAT2(a, b, c)
 extern "C" const tmpc::DimEntry *TM_CAT(tm_dim_entry_, TM_NX, TM_NU)() {
-    static const tmpc::DimEntry e = {TM_NX, TM_NU, &tmpc::launch, &tmpc::gpi_fit, &tmpc::gpi_ipc};
+    static const tmpc::DimEntry e = {TM_NX, TM_NU, &tmpc::launch, &tmpc::gpi_fit, &tmpc::gpi_ipc, &tmpc::precompute_batch};
     return &e;
 }

@@ -56,6 +56,9 @@ struct DimEntry {
     int (*gpi_fit)(int dtype, int N, int max_smem_optin);
     // GPI plan for (dtype, N): (warps per CTA << 16) | instances resident per CTA; 0 if GPI is not available
     int (*gpi_instances_per_cta)(int dtype, int N, int max_smem_optin);
+    // batched cache precompute on the device (precompute_kernel.cuh): device pointers, one model blob per instance
+    int (*precompute_batch)(int dtype, int64_t B, const void *A, const void *Bm, const void *f, const void *Qdiag, const void *Rdiag,
+                            const void *rho, void *models_out, int32_t *sweeps_out, int sm_count, cudaStream_t stream);
 };
 
 }  // namespace tmpc

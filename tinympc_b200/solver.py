@@ -150,6 +150,30 @@ class BatchedTinySolver:
         check(self._lib.tinympc_b200_solve_host(self._h, C.byref(cb)))
         return hb
 
+    def setup_models_device(self, A, B, f, Qdiag, Rdiag, rho, want_sweeps=False):
+        """setup_models on the GPU (tinympc_b200_precompute_cache_batch_device): inputs as in setup_models (numpy or torch,
+        A [Bn,nx,nx] / B [Bn,nx,nu] row index first), result = torch CUDA tensor [Bn, blob] usable as `models=` of
+        make_device_batch.  Bit-identical to the host routine."""
+        import torch
+
+        p = self.problem
+        tdt = torch.float32 if p.dtype == np.float32 else torch.float64
+        dev = torch.device("cuda", self.device)
+        t = lambda a: torch.as_tensor(a, device=dev).to(tdt)  # noqa: E731
+        A_ = t(A).reshape(-1, p.nx, p.nx).transpose(1, 2).contiguous()  # column-major per instance
+        Bn = A_.shape[0]
+        B_ = t(B).reshape(Bn, p.nx, p.nu).transpose(1, 2).contiguous()
+        f_, Q_, R_ = t(f).reshape(Bn, p.nx).contiguous(), t(Qdiag).reshape(Bn, p.nx).contiguous(), t(Rdiag).reshape(Bn, p.nu).contiguous()
+        r_ = t(rho).reshape(-1).expand(Bn).contiguous()
+        M = int(self._lib.tinympc_b200_model_blob_elems(p.nx, p.nu))
+        out = torch.zeros((Bn, M), dtype=tdt, device=dev)
+        sweeps = torch.zeros(Bn, dtype=torch.int32, device=dev) if want_sweeps else None
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        check(self._lib.tinympc_b200_precompute_cache_batch_device(
+            self._h, Bn, A_.data_ptr(), B_.data_ptr(), f_.data_ptr(), Q_.data_ptr(), R_.data_ptr(), r_.data_ptr(), out.data_ptr(),
+            None if sweeps is None else sweeps.data_ptr(), C.c_void_p(stream)))
+        return (out, sweeps) if want_sweeps else out
+
     # ---- device buffers (torch tensors on cuda:<device>) ---------------------------------------------
     def make_device_batch(self, x0, Xref, Uref=None, state=None, cold_start=True, want_state=(), want_residuals=True,
                           want_u0=False, want_solution=True, models=None):

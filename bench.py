@@ -326,7 +326,7 @@ def main():
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                      "kernel_ms": k_ms,
-                     "note": "compute/latency-bound by construction (SURVEY §8d); secondary: fp32 pipe",
+                     "note": "compute-bound by construction (SURVEY §8d: ~2000 flop per compulsory byte); ncu: issue slots 75% busy, fp32 pipe 67% of cycles active (profiles/r01_ncu_summary.md)",
                      "flops_achieved_tflops": flops / 1e12, "flops_frac_of_74.5_tflops_fp32": flops / 74.5e12},
         "clocks": clk,
     }

@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(TPI_THREADS, (sizeof(T) == 4 && !EXT) ? 4 : 2)
 
         // ---- backward_pass_grad fused with update_linear_cost ----
         for (int k = N - 2; k >= 0; --k) {
-            T q[NX], r[NU];
+            T q[NX], r[NU], tb[NU], pa_[NX];
             {
                 // every global load of this step is issued before the first use (a thread has no other way to overlap
                 // them: one dependent load round costs ~1 us and the EXT path used to have five per step)
@@ -305,6 +305,9 @@ __global__ void __launch_bounds__(TPI_THREADS, (sizeof(T) == 4 && !EXT) ? 4 : 2)
                     if (P.lin_u) { SU::load(P.w_zl, k, S, b, ez[1]); SU::load(P.w_yl, k, S, b, ey[1]); }
                     if (P.tvl_u) { SU::load(P.w_zlt, k, S, b, ez[2]); SU::load(P.w_ylt, k, S, b, ey[2]); }
                 }
+                // the two products that only need p_{k+1} run while those loads are in flight
+                dots_f<FAST, NU, NX>([&](int j, int i) { return P.Bm[i + NX * j]; }, p, tb);  // B^T p
+                dots_f<FAST, NX, NX>([&](int i, int m) { return P.AmBKt[i + NX * m]; }, p, pa_);
 #pragma unroll
                 for (int i = 0; i < NX; ++i) q[i] = nmac<FAST>(-(xr[i] * P.Qd[i]), rho, vn[i] - g[i]);
 #pragma unroll
@@ -325,15 +328,13 @@ __global__ void __launch_bounds__(TPI_THREADS, (sizeof(T) == 4 && !EXT) ? 4 : 2)
                 }
             }
             // d_k = Quu_inv * ((B^T p_{k+1} + r_k) + BPf)                                (admm.cpp:17)
-            T s[NU], d[NU], tb[NU];
-            dots_f<FAST, NU, NX>([&](int j, int i) { return P.Bm[i + NX * j]; }, p, tb);  // B^T p
+            T s[NU], d[NU];
 #pragma unroll
             for (int j = 0; j < NU; ++j) s[j] = (tb[j] + r[j]) + P.BPf[j];
             dots_f<FAST, NU, NU>([&](int j, int m) { return P.Quu[j + NU * m]; }, s, d);
             SU::store(P.w_d, k, S, b, d);
             // p_k = ((q_k + AmBKt p_{k+1}) - Kinf^T r_k) + APf                             (admm.cpp:18)
-            T pa_[NX], kr[NX];
-            dots_f<FAST, NX, NX>([&](int i, int m) { return P.AmBKt[i + NX * m]; }, p, pa_);
+            T kr[NX];
             dots_f<FAST, NX, NU>([&](int i, int j) { return P.Kinf[j + NU * i]; }, r, kr);
 #pragma unroll
             for (int i = 0; i < NX; ++i) p[i] = ((q[i] + pa_[i]) - kr[i]) + P.APf[i];
@@ -363,6 +364,12 @@ __global__ void __launch_bounds__(TPI_THREADS, (sizeof(T) == 4 && !EXT) ? 4 : 2)
                     if (P.lin_u) SU::load(P.w_yl, k, S, b, eyu[1]);
                     if (P.tvl_u) SU::load(P.w_ylt, k, S, b, eyu[2]);
                 }
+            }
+            // Kinf x_k and A x_k only need x_k: computed while the loads above are in flight
+            T kx[NU], ax[NX];
+            if (hasu) {
+                dots_f<FAST, NU, NX>([&](int j, int m) { return P.Kinf[j + NU * m]; }, x, kx);
+                dots_f<FAST, NX, NX>([&](int i, int m) { return P.A[i + NX * m]; }, x, ax);
             }
             {   // state column k
                 auto upd_x = [&](auto lo, auto hi) {  // vnew = clamp(x + g); g += x - vnew; residual maxima
@@ -419,12 +426,8 @@ __global__ void __launch_bounds__(TPI_THREADS, (sizeof(T) == 4 && !EXT) ? 4 : 2)
             }
             if (hasu) {  // input column k and the rollout step
                 T u[NU], zn[NU];
-                {   // u_k = -(Kinf x_k) - d_k                                              (admm.cpp:29)
-                    T kx[NU];
-                    dots_f<FAST, NU, NX>([&](int j, int m) { return P.Kinf[j + NU * m]; }, x, kx);
 #pragma unroll
-                    for (int j = 0; j < NU; ++j) u[j] = (-kx[j]) - d[j];
-                }
+                for (int j = 0; j < NU; ++j) u[j] = (-kx[j]) - d[j];  // u_k = -(Kinf x_k) - d_k    (admm.cpp:29)
                 auto upd_u = [&](auto lo, auto hi) {
 #pragma unroll
                     for (int j = 0; j < NU; ++j) {
@@ -477,8 +480,7 @@ __global__ void __launch_bounds__(TPI_THREADS, (sizeof(T) == 4 && !EXT) ? 4 : 2)
                     }
                 }
                 // x_{k+1} = (A x_k + B u_k) + f                                            (admm.cpp:30)
-                T ax[NX], bu[NX];
-                dots_f<FAST, NX, NX>([&](int i, int m) { return P.A[i + NX * m]; }, x, ax);
+                T bu[NX];
                 dots_f<FAST, NX, NU>([&](int i, int j) { return P.Bm[i + NX * j]; }, u, bu);
 #pragma unroll
                 for (int i = 0; i < NX; ++i) x[i] = (ax[i] + bu[i]) + P.f[i];

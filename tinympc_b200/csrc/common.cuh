@@ -50,6 +50,44 @@ __device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigne
     return r;
 }
 
+__device__ __forceinline__ unsigned long long sub2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+// element-wise o = a + b / o = a - b on short vectors.  fp32, even length: packed FADD2 (two IEEE additions per issued
+// instruction, bit-identical to two FADDs); anything else: scalar.
+template <typename T, int NV>
+__device__ __forceinline__ void vadd(const T (&a)[NV], const T (&b)[NV], T (&o)[NV]) {
+    constexpr int NP = (sizeof(T) == 4) ? NV / 2 * 2 : 0;  // elements handled as packed pairs
+    if constexpr (sizeof(T) == 4) {
+#pragma unroll
+        for (int e = 0; e < NP; e += 2) {
+            float lo, hi;
+            unpack2(add2(pack2((float)a[e], (float)a[e + 1]), pack2((float)b[e], (float)b[e + 1])), lo, hi);
+            o[e] = lo;
+            o[e + 1] = hi;
+        }
+    }
+#pragma unroll
+    for (int e = NP; e < NV; ++e) o[e] = a[e] + b[e];
+}
+template <typename T, int NV>
+__device__ __forceinline__ void vsub(const T (&a)[NV], const T (&b)[NV], T (&o)[NV]) {
+    constexpr int NP = (sizeof(T) == 4) ? NV / 2 * 2 : 0;
+    if constexpr (sizeof(T) == 4) {
+#pragma unroll
+        for (int e = 0; e < NP; e += 2) {
+            float lo, hi;
+            unpack2(sub2(pack2((float)a[e], (float)a[e + 1]), pack2((float)b[e], (float)b[e + 1])), lo, hi);
+            o[e] = lo;
+            o[e + 1] = hi;
+        }
+    }
+#pragma unroll
+    for (int e = NP; e < NV; ++e) o[e] = a[e] - b[e];
+}
+
 template <bool FAST, int NR, int NE>
 __device__ __forceinline__ void dots(const float (&M)[NR][NE], const float (&v)[NE], float (&out)[NR]) {
 #pragma unroll

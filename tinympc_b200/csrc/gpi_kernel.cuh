@@ -443,10 +443,30 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
         load_pb(k, pb);
     };
     auto cost_eval = [&](const T (&xr)[RX], const T (&ur)[RU], const T (&pa)[PVP], const T (&pb)[PVP], T (&q)[RX], T (&r)[RU]) {
+        if constexpr (FAST) {
 #pragma unroll
-        for (int a = 0; a < RX; ++a) q[a] = nmac<FAST>(-(xr[a] * vQd[a]), rho_(), pa[a] - pb[a]);
+            for (int a = 0; a < RX; ++a) q[a] = nmac<FAST>(-(xr[a] * vQd[a]), rho_(), pa[a] - pb[a]);
 #pragma unroll
-        for (int b = 0; b < RU; ++b) r[b] = nmac<FAST>(-(ur[b] * vRd[b]), rho_(), pa[RX + b] - pb[RX + b]);
+            for (int b = 0; b < RU; ++b) r[b] = nmac<FAST>(-(ur[b] * vRd[b]), rho_(), pa[RX + b] - pb[RX + b]);
+        } else {
+            // the same operations on the whole pack (state rows, input rows, padding): (-(ref*W)) - rho*(pa - pb), with the
+            // subtractions issued as packed pairs (fp32)
+            T m[PVP], df[PVP], t[PVP], o[PVP];
+#pragma unroll
+            for (int e = 0; e < PVP; ++e) m[e] = T(0);
+#pragma unroll
+            for (int a = 0; a < RX; ++a) m[a] = -(xr[a] * vQd[a]);
+#pragma unroll
+            for (int b = 0; b < RU; ++b) m[RX + b] = -(ur[b] * vRd[b]);
+            vsub<T, PVP>(pa, pb, df);
+#pragma unroll
+            for (int e = 0; e < PVP; ++e) t[e] = rho_() * df[e];
+            vsub<T, PVP>(m, t, o);
+#pragma unroll
+            for (int a = 0; a < RX; ++a) q[a] = o[a];
+#pragma unroll
+            for (int b = 0; b < RU; ++b) r[b] = o[RX + b];
+        }
     };
 
     // forward pass fused with slack / dual update / residuals.  SLOW = some slot is in the first iteration of a
@@ -480,30 +500,80 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
                     }
                 }
             }
-#pragma unroll
-            for (int a = 0; a < RX; ++a) {  // vnew = clamp(x + g), g += x - vnew
-                T vo = pa[a];
-                if constexpr (SLOW) {
-                    if (vin) vo = vprev[a];
+            if constexpr (FAST) {
+    #pragma unroll
+                for (int a = 0; a < RX; ++a) {  // vnew = clamp(x + g), g += x - vnew
+                    T vo = pa[a];
+                    if constexpr (SLOW) {
+                        if (vin) vo = vprev[a];
+                    }
+                    const T v = clamp_box<FAST>(xo[a] + pb[a], loX[a], hiX[a]);
+                    na[a] = v;
+                    nb[a] = (pb[a] + xo[a]) - v;
+                    rpx = absmax(rpx, xo[a] - v);
+                    rdx = absmax(rdx, vo - v);
                 }
-                const T v = clamp_box<FAST>(xo[a] + pb[a], loX[a], hiX[a]);
-                na[a] = v;
-                nb[a] = (pb[a] + xo[a]) - v;
-                rpx = absmax(rpx, xo[a] - v);
-                rdx = absmax(rdx, vo - v);
-            }
-            if (HASU) {
+                if (HASU) {
+    #pragma unroll
+                    for (int b = 0; b < RU; ++b) {
+                        T zo = pa[RX + b];
+                        if constexpr (SLOW) {
+                            if (vin) zo = vprev[RX + b];
+                        }
+                        const T z = clamp_box<FAST>(u[b] + pb[RX + b], loU[b], hiU[b]);
+                        na[RX + b] = z;
+                        nb[RX + b] = (pb[RX + b] + u[b]) - z;
+                        rpu = absmax(rpu, u[b] - z);
+                        rdu = absmax(rdu, zo - z);
+                    }
+                }
+            } else {
+                // the same update on the whole pack (state rows, input rows, padding) with the additions / subtractions
+                // issued as packed pairs (fp32): vnew = clamp(x + g), g' = (g + x) - vnew, residual differences
+                T X[PVP], lo[PVP], hi[PVP], vo[PVP], sum[PVP], v[PVP], dg[PVP], dx[PVP], dv[PVP];
+#pragma unroll
+                for (int e = 0; e < PVP; ++e) {
+                    X[e] = T(0);
+                    lo[e] = -kInf;
+                    hi[e] = kInf;
+                    vo[e] = pa[e];
+                    if constexpr (SLOW) {
+                        if (vin) vo[e] = vprev[e];
+                    }
+                }
+#pragma unroll
+                for (int a = 0; a < RX; ++a) {
+                    X[a] = xo[a];
+                    lo[a] = loX[a];
+                    hi[a] = hiX[a];
+                }
 #pragma unroll
                 for (int b = 0; b < RU; ++b) {
-                    T zo = pa[RX + b];
-                    if constexpr (SLOW) {
-                        if (vin) zo = vprev[RX + b];
+                    X[RX + b] = u[b];
+                    lo[RX + b] = loU[b];
+                    hi[RX + b] = hiU[b];
+                }
+                vadd<T, PVP>(X, pb, sum);
+#pragma unroll
+                for (int e = 0; e < PVP; ++e) v[e] = (e < RX + RU) ? clamp_box<FAST>(sum[e], lo[e], hi[e]) : sum[e];
+                vsub<T, PVP>(sum, v, dg);
+                vsub<T, PVP>(X, v, dx);
+                vsub<T, PVP>(vo, v, dv);
+#pragma unroll
+                for (int a = 0; a < RX; ++a) {
+                    na[a] = v[a];
+                    nb[a] = dg[a];
+                    rpx = absmax(rpx, dx[a]);
+                    rdx = absmax(rdx, dv[a]);
+                }
+                if (HASU) {
+#pragma unroll
+                    for (int b = 0; b < RU; ++b) {
+                        na[RX + b] = v[RX + b];
+                        nb[RX + b] = dg[RX + b];
+                        rpu = absmax(rpu, dx[RX + b]);
+                        rdu = absmax(rdu, dv[RX + b]);
                     }
-                    const T z = clamp_box<FAST>(u[b] + pb[RX + b], loU[b], hiU[b]);
-                    na[RX + b] = z;
-                    nb[RX + b] = (pb[RX + b] + u[b]) - z;
-                    rpu = absmax(rpu, u[b] - z);
-                    rdu = absmax(rdu, zo - z);
                 }
             }
             if constexpr (TM) store_pb(k, nb);  // (a slot that is not busy holds no live state)
@@ -558,8 +628,13 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
             gather_u(u, Uf);
             column(k, true, u, vprev, pbk);
             dots<FAST>(mB, Uf, bu);
+            {   // x_{k+1} = (A x_k + B u_k) + f
+                T ax[RX], tx[RX];
 #pragma unroll
-            for (int a = 0; a < RX; ++a) xo[a] = (t1[a] + bu[a]) + vf[a];  // x_{k+1} = (A x_k + B u_k) + f
+                for (int a = 0; a < RX; ++a) ax[a] = t1[a];
+                vadd<T, RX>(ax, bu, tx);
+                vadd<T, RX>(tx, vf, xo);
+            }
             gather_x(xo, Xf);
         }
         {
@@ -977,8 +1052,14 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
             gather_u(s_, Sf);
             // p_k = ((q_k + AmBKt p_{k+1}) - Kinf^T r_k) + APf
             dots<FAST>(mKt, Rf, kr);
+            {
+                T a1[RX], t1_[RX], t2_[RX];
 #pragma unroll
-            for (int a = 0; a < RX; ++a) po[a] = ((q[a] + acc1[a]) - kr[a]) + vAPf[a];
+                for (int a = 0; a < RX; ++a) a1[a] = acc1[a];
+                vadd<T, RX>(q, a1, t1_);
+                vsub<T, RX>(t1_, kr, t2_);
+                vadd<T, RX>(t2_, vAPf, po);
+            }
             if (MORE) gather_x(po, Pf);  // p_0 itself is never used (the forward pass starts from x_0)
             dots<FAST>(mQuu, Sf, dq);
             store_d(k, dq, busy);

@@ -45,8 +45,11 @@ extern "C" {
 /* kernel family selection (TINYMPC_KERNEL_AUTO picks the fastest that fits) */
 #define TINYMPC_KERNEL_AUTO 0
 #define TINYMPC_KERNEL_TPI 1 /* thread-per-instance, state streamed through HBM/L2 (any feature set)   */
-#define TINYMPC_KERNEL_GPI 2 /* lane-group-per-instance, state resident in shared memory (box only)    */
-#define TINYMPC_KERNEL_HYBRID 3 /* GPI and TPI co-resident on every SM, batch split between them        */
+#define TINYMPC_KERNEL_GPI 2 /* lane-group-per-instance: state resident on chip (shared + tensor memory) when the   */
+                             /* problem is box-constrained and fits, else the streamed variant below               */
+/* 3 was an experimental split of a batch between the GPI and TPI kernels; removed (it never won, see profiles/) */
+#define TINYMPC_KERNEL_GPS 4 /* lane-group-per-instance, state streamed through an L2/HBM workspace behind a       */
+                             /* cp.async ring (any feature set: box, cones, hyperplanes; fp32 and fp64)            */
 
 /* error codes */
 #define TINYMPC_OK 0
@@ -55,6 +58,7 @@ extern "C" {
 #define TINYMPC_ERR_CUDA (-3)        /* CUDA runtime error (message in tinympc_b200_last_error)        */
 #define TINYMPC_ERR_NO_BOUNDS (-4)   /* en_*_bound set but bounds were never provided (UB in the ref.) */
 #define TINYMPC_ERR_CONE_DIM (-5)    /* cone dimension != 3 (the reference only supports 3, admm.cpp:53)*/
+#define TINYMPC_ERR_SINGULAR (-6)    /* batched precompute: R + B'PB singular for some instance (index in last_error) */
 
 /*
  * Problem description = the read-only part of the reference's
@@ -178,15 +182,16 @@ typedef struct tinympc_b200_stats {
     int64_t instances;
     int64_t kernel_launches; /* launches of this library's kernels in the last solve call */
     float kernel_ms;         /* device time of the solve kernel(s), CUDA events on the launch stream */
-    int32_t kernel_family;   /* TINYMPC_KERNEL_TPI / _GPI actually used */
+    int32_t kernel_family;   /* TINYMPC_KERNEL_TPI / _GPI / _GPS actually used */
     int32_t lanes_per_instance;
     int32_t instances_per_cta;
     int32_t smem_bytes_per_cta;
     int32_t ctas;
     int32_t threads_per_cta;
-    int64_t gpi_instances; /* HYBRID: how many instances of the batch the GPI kernel took (rest: TPI) */
+    int64_t gpi_instances; /* instances of the batch solved by a lane-group kernel (GPI or GPS) */
     int32_t tmem_cols_per_cta; /* GPI: tensor-memory columns holding the dual variables and d (0 = all in shared memory) */
     int32_t reserved0;
+    int64_t workspace_bytes; /* GPS / TPI: bytes of streamed-state workspace behind the last solve (0 = state on chip) */
 } tinympc_b200_stats_t;
 
 /* tiny_set_default_settings (tiny_api.cpp:413-441, tiny_api_constants.hpp:5-16) */
@@ -213,7 +218,8 @@ int64_t tinympc_b200_model_blob_elems(int32_t nx, int32_t nu);
  *   cache_b = tiny_precompute_and_set_cache(A[b], B[b], f[b], Q_b, R_b, rho[b])   (tiny_api.cpp:307-381)
  * packed into models_out[b] (layout: tinympc_batch_t.models).  A [B][nx*nx], Bm [B][nx*nu] column-major, f [B][nx],
  * Qdiag [B][nx], Rdiag [B][nu] (the USER's diagonals, without rho), rho [B]; all in `dtype`.
- * Returns 0, or the (1-based) index of the first instance whose Riccati recursion hit a singular matrix, negated.
+ * Returns 0, or TINYMPC_ERR_SINGULAR when some instance's Riccati recursion hit a singular matrix (the index of the
+ * first such instance is in tinympc_b200_last_error()).
  */
 int tinympc_b200_precompute_cache_batch(int32_t dtype, int32_t nx, int32_t nu, int64_t B, const void *A, const void *Bm,
                                         const void *f, const void *Qdiag, const void *Rdiag, const void *rho,

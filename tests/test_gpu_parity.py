@@ -17,9 +17,11 @@ from tinympc_b200.solver import BatchedTinySolver, setup_problem
 
 pytestmark = pytest.mark.gpu
 
-# "gpi" = the planner's choice (dual variables + d in tensor memory when that holds more instances per SM);
-# "gpi_smem" forces the all-shared-memory variant (TINYMPC_GPI_TMEM=0)
-KERNELS = {"tpi": abi.KERNEL_TPI, "gpi": abi.KERNEL_GPI, "gpi_smem": abi.KERNEL_GPI, "hybrid": abi.KERNEL_HYBRID, "auto": abi.KERNEL_AUTO}
+# "gpi" = the lane-group kernels, planner's choice: state on chip (dual variables + d in tensor memory when that holds
+# more instances per SM) for box-constrained problems that fit, else the streamed variant;
+# "gpi_smem" forces the all-shared-memory on-chip variant (TINYMPC_GPI_TMEM=0); "gps" forces the streamed variant
+KERNELS = {"tpi": abi.KERNEL_TPI, "gpi": abi.KERNEL_GPI, "gpi_smem": abi.KERNEL_GPI, "gps": abi.KERNEL_GPS, "auto": abi.KERNEL_AUTO}
+ALLK = ["tpi", "gpi", "gpi_smem", "gps"]
 
 
 @pytest.fixture(autouse=True)
@@ -59,22 +61,27 @@ def _gpi_applicable(prob, st):
     return not ext
 
 
-@pytest.mark.parametrize("kernel", ["tpi", "gpi", "gpi_smem"])
+@pytest.mark.parametrize("kernel", ALLK)
 @pytest.mark.parametrize("name", H.golden_names())
 def test_strict_bit_identical_to_reference_golden(name, kernel):
     prob, st, inst, meta, gold = H.load_golden(name)
-    if kernel.startswith("gpi") and not _gpi_applicable(prob, st):
-        pytest.skip("GPI kernel covers box constraints only (cones/hyperplanes run on the TPI kernel)")
+    boxonly = _gpi_applicable(prob, st)
+    if kernel == "gpi_smem" and not boxonly:
+        pytest.skip("cones / hyperplanes always stream their state: covered by the 'gpi' and 'gps' cases")
     solver = _mk_solver(prob, st, kernel)
     got, _ = H.closed_loop(prob, st, inst, meta["steps"], meta["reset_duals"], meta["state"], _cuda_fn(solver),
                            x0_seq=meta["x0_seq"])
     for k, (g, r) in enumerate(zip(gold, got)):
         for key in H.OUT_KEYS + meta["state"]:
             assert H.bits_equal(g[key], r[key]), f"{name}/{kernel} step {k}: {key} differs from the reference"
-    assert solver.stats()["kernel_family"] == KERNELS[kernel]
+    fam = solver.stats()["kernel_family"]
+    if kernel == "gpi":  # on chip when the problem is box-constrained (every golden horizon fits), else streamed lane groups
+        assert fam == (abi.KERNEL_GPI if boxonly else abi.KERNEL_GPS)
+    else:
+        assert fam == KERNELS[kernel]
 
 
-@pytest.mark.parametrize("kernel", ["tpi", "gpi", "gpi_smem"])
+@pytest.mark.parametrize("kernel", ALLK)
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
 def test_strict_batch_vs_oracle_ragged(dt, kernel):
     """A ragged batch (B not a multiple of the warp / group size) of randomised tracking instances, cold start,
@@ -101,7 +108,7 @@ def test_strict_batch_vs_oracle_ragged(dt, kernel):
         assert H.bits_equal(g2[key], o2[key]), "warm " + key
 
 
-@pytest.mark.parametrize("kernel", ["tpi", "gpi", "gpi_smem"])
+@pytest.mark.parametrize("kernel", ALLK)
 def test_edge_cases(kernel):
     """B=1, B=33; max_iter=1; check_termination=3 (stale residual fields); per-instance Uref; shared refs."""
     spec = wl.quadrotor(N=10)
@@ -121,7 +128,7 @@ def test_edge_cases(kernel):
             assert H.bits_equal(g[key], o[key]), (B, max_iter, check, key)
 
 
-@pytest.mark.parametrize("kernel", ["tpi", "gpi", "gpi_smem"])
+@pytest.mark.parametrize("kernel", ALLK)
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
 def test_fast_mode_within_reference_scatter(dt, kernel):
     """FAST mode = same operation order with FMA contraction.  It cannot be bit-identical to any Eigen build
@@ -162,7 +169,7 @@ def test_fast_mode_within_reference_scatter(dt, kernel):
     assert g2["iter"].mean() <= 1.1 * o2["iter"].mean() + 0.5
 
 
-@pytest.mark.parametrize("kernel", ["tpi", "gpi", "gpi_smem"])
+@pytest.mark.parametrize("kernel", ALLK)
 def test_device_pointer_path_equals_host_path(kernel):
     import torch
 
@@ -192,10 +199,10 @@ def test_full_size_identical_instances_and_shard_invariance():
     B = 65536
     inst = wl.hovering_instances(B, N=50, dtype=dt)
     o = _port(prob, st, inst["x0"][:1], inst["Xref"], None, None, True, ("u",), nthreads=1)
-    for kernel in ("gpi", "gpi_smem", "tpi", "hybrid"):
+    for kernel in ("gpi", "gpi_smem", "tpi", "gps"):
         solver = _mk_solver(prob, st, kernel)
         g = solver.solve(inst["x0"], inst["Xref"], None, cold_start=True, want_state=("u",))
-        if kernel.startswith("gpi"):
+        if kernel in ("gpi", "gpi_smem"):
             # (12,4,50) fp32: g, y and d (5 columns per knot point and thread) fit in tensor memory for 8 warps per SM,
             # twice what shared memory alone holds
             stt = solver.stats()
@@ -209,24 +216,31 @@ def test_full_size_identical_instances_and_shard_invariance():
         assert int(g["iter"].sum()) == 100 * B and not g["solved"].any()  # runs to max_iter
 
 
-def test_full_size_tracking_sample_vs_oracle():
-    """BASELINE config 3 at full size (B=65536 randomised tracking instances): the oracle is run on a strided
-    sample of 512 instances; iteration histogram sanity on the whole batch."""
+@pytest.mark.parametrize("kernel", ["auto", "gps"])
+def test_full_size_tracking_sample_vs_oracle(kernel):
+    """BASELINE config 3 at full size (B=65536 randomised tracking instances, per-instance references) on the path the
+    bench numbers come from (AUTO = on-chip lane groups with tensor memory) and on the streamed lane groups: the oracle is
+    run on a strided sample of 512 instances; iteration histogram sanity on the whole batch."""
+    import torch
+
     spec = wl.quadrotor(N=50)
     dt = np.float32
     prob = setup_problem(spec, dt)
     st = spec.settings
     B = 65536
     inst = wl.tracking_instances(B, N=50, seed=0, dtype=dt)
-    solver = _mk_solver(prob, st, "hybrid")  # GPI and TPI co-resident on every SM, batch split between them
+    solver = _mk_solver(prob, st, kernel)
     batch, out = solver.make_device_batch(inst["x0"], inst["Xref"], None, cold_start=True)
     solver.solve_device(batch)
-    import torch
     torch.cuda.synchronize()
     stt = solver.stats()
-    assert stt["kernel_family"] == abi.KERNEL_HYBRID and stt["kernel_launches"] == 2 and 0 < stt["gpi_instances"] < B
+    if kernel == "auto":
+        assert stt["kernel_family"] == abi.KERNEL_GPI and stt["tmem_cols_per_cta"] == 512 and stt["instances_per_cta"] == 64
+    else:
+        assert stt["kernel_family"] == abi.KERNEL_GPS and stt["workspace_bytes"] > 0
+    assert stt["kernel_launches"] == 1
     g = {k: v.cpu().numpy() for k, v in out.items() if v is not None}
-    idx = np.unique(np.concatenate([np.arange(0, B, B // 512), np.arange(stt["gpi_instances"] - 8, stt["gpi_instances"] + 8)]))
+    idx = np.unique(np.concatenate([np.arange(0, B, B // 512), np.arange(B - 8, B)]))
     o = _port(prob, st, inst["x0"][idx], inst["Xref"][idx], None, None, True, ())
     for key in H.OUT_KEYS:
         assert H.bits_equal(g[key][idx], o[key]), key
@@ -244,17 +258,32 @@ def test_errors_are_loud():
     with pytest.raises(TinyMPCError) as e:
         solver.solve(inst["x0"], inst["Xref"])
     assert e.value.code == abi.ERR_NO_BOUNDS
-    # cones force the TPI kernel; asking for GPI explicitly is refused
+    # overlapping cones: the reference applies them one after the other (admm.cpp:115-121); the lane-group kernels project
+    # the cones of a knot point independently and refuse, AUTO falls back to the thread-per-instance kernel
     rs = wl.rocket(N=10)
+    rs.constraints = dict(rs.constraints, Acx=[0, 2], qcx=[3, 3], cx=[0.25, 0.5])
     rp = setup_problem(rs, np.float64)
-    s2 = BatchedTinySolver(rp, rs.settings, kernel=abi.KERNEL_GPI)
     ri = wl.rocket_instances(2, N=10)
-    with pytest.raises(TinyMPCError) as e:
-        s2.solve(ri["x0"], ri["Xref"], ri["Uref"])
-    assert e.value.code == abi.ERR_UNSUPPORTED
+    for k in (abi.KERNEL_GPS, abi.KERNEL_GPI):
+        s2 = BatchedTinySolver(rp, rs.settings, kernel=k)
+        with pytest.raises(TinyMPCError) as e:
+            s2.solve(ri["x0"], ri["Xref"], ri["Uref"])
+        assert e.value.code == abi.ERR_UNSUPPORTED
+    s3 = BatchedTinySolver(rp, rs.settings, kernel=abi.KERNEL_AUTO)
+    g = s3.solve(ri["x0"], ri["Xref"], ri["Uref"])
+    o = _port(rp, rs.settings, ri["x0"], ri["Xref"], ri["Uref"], None, True, ())
+    assert s3.stats()["kernel_family"] == abi.KERNEL_TPI and H.bits_equal(g["sol_u"], o["sol_u"])
+    # hyperplane count without its matrices is an argument error at create(), not a device fault later
+    bad = setup_problem(wl.quadrotor(N=10), np.float32)
+    cp = bad.to_c()
+    cp.num_state_linear = 2
+    import ctypes as C
+    from tinympc_b200._lib import load
+    h = C.c_void_p()
+    assert load().tinympc_b200_create(C.byref(cp), 0, C.byref(h)) == abi.ERR_ARG
 
 
-@pytest.mark.parametrize("kernel", ["tpi", "gpi", "gpi_smem"])
+@pytest.mark.parametrize("kernel", ALLK)
 def test_device_resident_closed_loop_matches_oracle(kernel):
     """the reference's closed loop (set x0 -> solve warm-started -> x0 = A x0 + B u0) for 300 plants kept
     entirely on the GPU (DeviceMPCLoop + tinympc_b200_advance) equals the oracle stepping the same loop on the host."""
@@ -296,7 +325,7 @@ def test_device_resident_closed_loop_matches_oracle(kernel):
         assert H.bits_equal(loop.x0.cpu().numpy(), x0), ("advance", k)
 
 
-@pytest.mark.parametrize("kernel", ["tpi", "gpi", "gpi_smem"])
+@pytest.mark.parametrize("kernel", ALLK)
 @pytest.mark.parametrize("dims", [(4, 2), (4, 8), (6, 3), (8, 8), (12, 2), (12, 8), (16, 2), (16, 4), (16, 8)])
 def test_every_compiled_dimension_vs_oracle(dims, kernel):
     """Random LTI problems for the other compiled (nx, nu) pairs (lane mappings L=4 and L=8, padding rows),
@@ -319,7 +348,7 @@ def test_every_compiled_dimension_vs_oracle(dims, kernel):
         assert (np.abs(o["znew"]) >= 1.0 - 1e-6).any()  # the box was active somewhere
 
 
-@pytest.mark.parametrize("kernel", ["tpi", "gpi", "gpi_smem"])
+@pytest.mark.parametrize("kernel", ALLK)
 def test_time_varying_bounds(kernel):
     """Bounds are full nx x N / nu x (N-1) matrices in the reference API (types.hpp:117-120); every example passes
     constants, here they really vary along the horizon."""
@@ -344,7 +373,7 @@ def test_time_varying_bounds(kernel):
         assert H.bits_equal(g[key], o[key]), key
 
 
-@pytest.mark.parametrize("kernel", ["tpi", "gpi", "gpi_smem"])
+@pytest.mark.parametrize("kernel", ALLK)
 def test_max_iter_zero_returns_the_warm_state(kernel):
     """max_iter = 0: solve() skips its loop (admm.cpp:378) and reports solution = vnew/znew as they stand, iter = 0."""
     spec = wl.quadrotor(N=10)
@@ -365,7 +394,7 @@ def test_max_iter_zero_returns_the_warm_state(kernel):
     assert (g["iter"] == 0).all() and H.bits_equal(g["sol_x"], first["vnew"])
 
 
-@pytest.mark.parametrize("kernel", ["tpi", "gpi", "gpi_smem"])
+@pytest.mark.parametrize("kernel", ALLK)
 @pytest.mark.parametrize("N", [2, 3, 5])
 def test_tiny_horizons(N, kernel):
     """N = 2 is the smallest horizon the reference can represent (one input column)."""

@@ -7,10 +7,10 @@ import ctypes as C
 
 F32, F64 = 0, 1
 MODE_STRICT, MODE_FAST = 0, 1
-KERNEL_AUTO, KERNEL_TPI, KERNEL_GPI, KERNEL_HYBRID = 0, 1, 2, 3
+KERNEL_AUTO, KERNEL_TPI, KERNEL_GPI, KERNEL_GPS = 0, 1, 2, 4
 
 OK = 0
-ERR_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_NO_BOUNDS, ERR_CONE_DIM = -1, -2, -3, -4, -5
+ERR_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_NO_BOUNDS, ERR_CONE_DIM, ERR_SINGULAR = -1, -2, -3, -4, -5, -6
 
 vp = C.c_void_p
 i32p = C.POINTER(C.c_int32)
@@ -81,6 +81,7 @@ class Stats(C.Structure):
         ("ctas", C.c_int32), ("threads_per_cta", C.c_int32),
         ("gpi_instances", C.c_int64),
         ("tmem_cols_per_cta", C.c_int32), ("reserved0", C.c_int32),
+        ("workspace_bytes", C.c_int64),
     ]
 
 

@@ -132,16 +132,21 @@ struct tinympc_b200_solver {
     tinympc_settings_t settings;
     int mode = TINYMPC_MODE_STRICT;
     int family = TINYMPC_KERNEL_AUTO;
-    // workspace
+    bool cones_disjoint = true;  // the lane-group kernels project the cones of a knot point independently
+    // workspace (one solve at a time per handle: enqueue() serialises launches issued on different streams)
     DevBuf ws;
     DevBuf queue;
     DevBuf vscratch;
+    DevBuf gps_ws;
+    DevBuf shared_ref;  // host path: references shared by the whole batch
+    cudaEvent_t ev_last = nullptr;  // recorded after the last enqueue
+    cudaStream_t last_stream = nullptr;
+    bool have_last = false;
     // host-path staging (per pipeline slot)
     static constexpr int SLOTS = 3;
     DevBuf dio[SLOTS];
     PinBuf pin_in[SLOTS], pin_out[SLOTS];
-    cudaStream_t st_h2d = nullptr, st_k = nullptr, st_d2h = nullptr, st_a = nullptr, st_b = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_ja = nullptr, ev_jb = nullptr;
+    cudaStream_t st_h2d = nullptr, st_k = nullptr, st_d2h = nullptr;
     cudaEvent_t ev_in[SLOTS] = {}, ev_k[SLOTS] = {}, ev_out[SLOTS] = {};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
@@ -176,11 +181,17 @@ int check_ready(const tinympc_b200_solver *s) {
     const tinympc_settings_t &st = s->settings;
     if ((st.en_state_bound && !s->has_xb) || (st.en_input_bound && !s->has_ub))
         return fail(TINYMPC_ERR_NO_BOUNDS, "en_state_bound/en_input_bound set but bounds were never provided");
-    if (st.en_state_linear && s->nlx > 0 && !s->d_Alin_x.p) return fail(TINYMPC_ERR_ARG, "state linear constraints enabled but not set");
+    if ((st.en_state_linear && s->nlx > 0 && (!s->d_Alin_x.p || !s->d_blin_x.p)) || (st.en_input_linear && s->nlu > 0 && (!s->d_Alin_u.p || !s->d_blin_u.p)) ||
+        (st.en_tv_state_linear && s->ntvx > 0 && (!s->d_tvA_x.p || !s->d_tvb_x.p)) || (st.en_tv_input_linear && s->ntvu > 0 && (!s->d_tvA_u.p || !s->d_tvb_u.p)))
+        return fail(TINYMPC_ERR_ARG, "linear constraints enabled but their matrices were not uploaded");
     if (st.check_termination <= 0) return fail(TINYMPC_ERR_ARG, "check_termination must be >= 1");
     return 0;
 }
 
+// Which kernel family serves a solve.  GPI = lane groups, state on chip (box constraints, horizon fits in shared + tensor
+// memory); GPS = lane groups, state streamed (everything else the lane mapping covers); TPI = one thread per instance.
+// `smem_out`: shared-memory bytes of the on-chip plan (0 = not available).  Returns -1 when an explicit request cannot
+// be honoured.
 int resolve_family(const tinympc_b200_solver *s, const Features &ft, int *smem_out, int64_t B = 0) {
     int smem = 0;
     bool gpi_ok = false;
@@ -189,11 +200,14 @@ int resolve_family(const tinympc_b200_solver *s, const Features &ft, int *smem_o
         gpi_ok = smem > 0;
     }
     if (smem_out) *smem_out = smem;
-    if (s->family == TINYMPC_KERNEL_GPI) return gpi_ok ? TINYMPC_KERNEL_GPI : -1;
+    const bool gps_ok = s->dim->gps_lanes && s->dim->gps_lanes(s->dtype) > 0 && (!(ft.soc_x || ft.soc_u) || s->cones_disjoint);
+    if (s->family == TINYMPC_KERNEL_GPI) return gpi_ok ? TINYMPC_KERNEL_GPI : (gps_ok ? TINYMPC_KERNEL_GPS : -1);
+    if (s->family == TINYMPC_KERNEL_GPS) return gps_ok ? TINYMPC_KERNEL_GPS : -1;
     if (s->family == TINYMPC_KERNEL_TPI) return TINYMPC_KERNEL_TPI;
-    if (s->family == TINYMPC_KERNEL_HYBRID) return gpi_ok ? TINYMPC_KERNEL_HYBRID : -1;
+    // AUTO
+    if (ft.ext) return gps_ok ? TINYMPC_KERNEL_GPS : TINYMPC_KERNEL_TPI;  // measured: profiles/r02_* (rocket landing, 3-4x)
     if (!gpi_ok) return TINYMPC_KERNEL_TPI;
-    // AUTO: GPI unless on-chip memory (shared + tensor memory) holds fewer than 32 instances per SM (long horizons with
+    // GPI unless on-chip memory (shared + tensor memory) holds fewer than 32 instances per SM (long horizons with
     // wide inputs) AND the batch is large enough to fill the GPU with one thread per instance.  Measured on B200
     // (profiles/r01_sweep_1gpu.md, B = 131 072, N = 100): at 16 instances/SM TPI wins by 10-35 % for every shape except
     // (16,8), where its register footprint costs more than the low GPI occupancy; at >= 32 instances/SM GPI always wins.
@@ -202,17 +216,6 @@ int resolve_family(const tinympc_b200_solver *s, const Features &ft, int *smem_o
     const bool tpi_heavy = s->nx >= 16 && s->nu >= 8;
     if (ipc > 0 && ipc < 32 && !tpi_heavy && B >= (int64_t)s->sm_count * 384) return TINYMPC_KERNEL_TPI;
     return TINYMPC_KERNEL_GPI;
-}
-
-// Fraction of a batch the GPI kernel takes in HYBRID mode.  GPI (shared-memory bound: one CTA per SM, 4 warps,
-// no HBM traffic) and TPI (register/HBM bound, no shared memory) fit on an SM together; measured split in
-// profiles/ (override with TINYMPC_HYBRID_GPI_FRACTION for experiments).
-double hybrid_fraction(const tinympc_b200_solver *s) {
-    if (const char *e = std::getenv("TINYMPC_HYBRID_GPI_FRACTION")) {
-        double v = std::atof(e);
-        if (v >= 0.0 && v <= 1.0) return v;
-    }
-    return s->dtype == TINYMPC_F32 ? 0.55 : 0.5;
 }
 
 // carve the TPI structure-of-arrays workspace
@@ -326,104 +329,82 @@ int enqueue(tinympc_b200_solver *s, const tinympc_batch_t *io, cudaStream_t stre
     int smem = 0;
     int family = resolve_family(s, ft, &smem, io->B);
     if (io->models) {  // per-instance models: on-chip kernel only
-        if (ft.ext || smem <= 0 || s->family == TINYMPC_KERNEL_TPI)
-            return fail(TINYMPC_ERR_UNSUPPORTED, "per-instance models need the GPI kernel (box constraints, horizon fitting in shared memory)");
+        if (ft.ext || smem <= 0 || s->family == TINYMPC_KERNEL_TPI || s->family == TINYMPC_KERNEL_GPS)
+            return fail(TINYMPC_ERR_UNSUPPORTED, "per-instance models need the on-chip GPI kernel (box constraints, horizon fitting in shared memory)");
         family = TINYMPC_KERNEL_GPI;
     }
-    if (family < 0) return fail(TINYMPC_ERR_UNSUPPORTED, "GPI kernel requested but it does not support this problem (features or shared-memory footprint)");
+    if (family < 0) return fail(TINYMPC_ERR_UNSUPPORTED, "the requested lane-group kernel does not cover this problem (shape, or overlapping cones)");
+    // The launch scratch of a handle (work queue, workspaces, timing events) is single-buffered: a solve enqueued on a
+    // different stream than the previous one first waits for it.
+    if (s->have_last && s->last_stream != stream) CUDA_TRY(cudaStreamWaitEvent(stream, s->ev_last, 0));
     int64_t launches = 0, ctas = 0;
+    size_t ws_bytes = 0;
     tmpc::LaunchDesc d;
     base_desc(s, d, ft);
     if (timed) CUDA_TRY(cudaEventRecord(s->ev0, stream));
-    // instances [0, Bg) go to the GPI kernel, [Bg, B) to the TPI kernel
-    int64_t Bg = family == TINYMPC_KERNEL_GPI ? io->B : 0;
-    if (family == TINYMPC_KERNEL_HYBRID) {
-        const int64_t min_each = (int64_t)s->sm_count * 64;
-        Bg = (int64_t)(hybrid_fraction(s) * (double)io->B) / 32 * 32;
-        if (io->B < 2 * min_each || Bg < min_each) Bg = io->B;           // too small to split: GPI alone
-        else if (io->B - Bg < min_each) Bg = io->B;
-    }
-    const int64_t Bt = io->B - Bg;
-    const bool split = Bg > 0 && Bt > 0;
-    cudaStream_t sg = stream, stt = stream;
-    if (split) {
-        if (!s->st_a) {
-            CUDA_TRY(cudaStreamCreateWithFlags(&s->st_a, cudaStreamNonBlocking));
-            CUDA_TRY(cudaStreamCreateWithFlags(&s->st_b, cudaStreamNonBlocking));
-            CUDA_TRY(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
-            CUDA_TRY(cudaEventCreateWithFlags(&s->ev_ja, cudaEventDisableTiming));
-            CUDA_TRY(cudaEventCreateWithFlags(&s->ev_jb, cudaEventDisableTiming));
-        }
-        CUDA_TRY(cudaEventRecord(s->ev_fork, stream));
-        CUDA_TRY(cudaStreamWaitEvent(s->st_a, s->ev_fork, 0));
-        CUDA_TRY(cudaStreamWaitEvent(s->st_b, s->ev_fork, 0));
-        sg = s->st_a;
-        stt = s->st_b;
-    }
-    if (Bg > 0) {
-        d.family = TINYMPC_KERNEL_GPI;
-        d.stream = sg;
+    d.family = family;
+    d.stream = stream;
+    if (family == TINYMPC_KERNEL_GPI || family == TINYMPC_KERNEL_GPS) {
         if (s->queue.ensure(256)) return fail(TINYMPC_ERR_CUDA, "queue allocation failed");
-        CUDA_TRY(cudaMemsetAsync(s->queue.p, 0, 256, sg));
+        CUDA_TRY(cudaMemsetAsync(s->queue.p, 0, 256, stream));
         d.work_queue = s->queue.p;
         d.gpi_vscratch = nullptr;
-        if (io->state.v || io->state.z) {  // previous-iteration slacks are staged in pack layout, one 16-byte store per knot point
+        if (family == TINYMPC_KERNEL_GPI && (io->state.v || io->state.z)) {  // previous-iteration slacks are staged in pack layout, one 16-byte store per knot point
             const int plan = s->dim->gpi_instances_per_cta(s->dtype, s->N, s->max_smem_optin);
             const int warps = plan >> 16, ipc = plan & 0xffff;
             const int L = (warps > 0 && ipc > 0) ? 32 * warps / ipc : 4;
             const int W = s->dtype == TINYMPC_F64 ? 2 : 4;
             const int pv = (s->nx + L - 1) / L + (s->nu + L - 1) / L;
             const size_t pvp = (size_t)(pv + W - 1) / W * W;
-            if (s->vscratch.ensure((size_t)Bg * s->N * L * pvp * esize(s->dtype) + 256)) return fail(TINYMPC_ERR_CUDA, "GPI v-scratch allocation failed");
+            if (s->vscratch.ensure((size_t)io->B * s->N * L * pvp * esize(s->dtype) + 256)) return fail(TINYMPC_ERR_CUDA, "GPI v-scratch allocation failed");
             d.gpi_vscratch = s->vscratch.p;
         }
-        d.Bpad = (Bg + 31) / 32 * 32;
-        d.io = slice_batch(s, *io, 0, Bg);
+        d.Bpad = (io->B + 31) / 32 * 32;
+        d.io = *io;
+        d.gps_ws = s->gps_ws.p;
+        d.gps_ws_bytes = s->gps_ws.bytes;
         int rc = s->dim->launch(&d);
+        if (rc == tmpc::TM_ERR_WORKSPACE) {  // the streamed kernel sizes its workspace by resident slots: grow and retry
+            if (s->have_last) CUDA_TRY(cudaEventSynchronize(s->ev_last));  // a previous solve may still use the old buffer
+            if (s->gps_ws.ensure(d.out_ws_need + 256)) return fail(TINYMPC_ERR_CUDA, "GPS workspace allocation failed");
+            d.gps_ws = s->gps_ws.p;
+            d.gps_ws_bytes = s->gps_ws.bytes;
+            rc = s->dim->launch(&d);
+        }
         if (rc == TINYMPC_ERR_CUDA) return fail(rc, std::string("kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
-        if (rc) return fail(rc, "no compiled kernel for this (dtype, mode, family) combination");
+        if (rc) return fail(TINYMPC_ERR_UNSUPPORTED, "no compiled kernel for this (dtype, mode, family) combination");
         ++launches;
         ctas += d.out_ctas;
-        s->stats.lanes_per_instance = d.out_lanes_per_instance;
-        s->stats.instances_per_cta = d.out_instances_per_cta;
-        s->stats.smem_bytes_per_cta = d.out_smem;
-        s->stats.threads_per_cta = d.out_threads;
-        s->stats.tmem_cols_per_cta = d.out_tmem_cols;
-    }
-    if (Bt > 0) {
-        d.family = TINYMPC_KERNEL_TPI;
-        d.stream = stt;
-        const int64_t chunk = tpi_chunk_instances(s, ft, Bt);
+        if (family == TINYMPC_KERNEL_GPS) ws_bytes = d.out_ws_need;
+    } else {
+        const int64_t chunk = tpi_chunk_instances(s, ft, io->B);
         if (int rc = setup_workspace(s, d, ft, chunk, TINYMPC_KERNEL_TPI)) return rc;
-        for (int64_t b0 = 0; b0 < Bt; b0 += chunk) {
-            d.io = slice_batch(s, *io, Bg + b0, std::min<int64_t>(chunk, Bt - b0));
+        ws_bytes = s->ws.bytes;
+        for (int64_t b0 = 0; b0 < io->B; b0 += chunk) {
+            d.io = slice_batch(s, *io, b0, std::min<int64_t>(chunk, io->B - b0));
             int rc = s->dim->launch(&d);
             if (rc == TINYMPC_ERR_CUDA) return fail(rc, std::string("kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
             if (rc) return fail(rc, "no compiled kernel for this (dtype, mode, family) combination");
             ++launches;
             ctas += d.out_ctas;
         }
-        if (Bg == 0) {
-            s->stats.lanes_per_instance = d.out_lanes_per_instance;
-            s->stats.instances_per_cta = d.out_instances_per_cta;
-            s->stats.smem_bytes_per_cta = d.out_smem;
-            s->stats.threads_per_cta = d.out_threads;
-            s->stats.tmem_cols_per_cta = 0;
-        }
     }
-    if (split) {
-        CUDA_TRY(cudaEventRecord(s->ev_ja, s->st_a));
-        CUDA_TRY(cudaEventRecord(s->ev_jb, s->st_b));
-        CUDA_TRY(cudaStreamWaitEvent(stream, s->ev_ja, 0));
-        CUDA_TRY(cudaStreamWaitEvent(stream, s->ev_jb, 0));
-    }
+    s->stats.lanes_per_instance = d.out_lanes_per_instance;
+    s->stats.instances_per_cta = d.out_instances_per_cta;
+    s->stats.smem_bytes_per_cta = d.out_smem;
+    s->stats.threads_per_cta = d.out_threads;
+    s->stats.tmem_cols_per_cta = d.out_tmem_cols;
     if (timed) CUDA_TRY(cudaEventRecord(s->ev1, stream));
+    CUDA_TRY(cudaEventRecord(s->ev_last, stream));
+    s->last_stream = stream;
+    s->have_last = true;
     s->timed = timed;
     s->stats.instances = io->B;
     s->stats.kernel_launches = launches;
-    s->stats.kernel_family = split ? TINYMPC_KERNEL_HYBRID : (Bg > 0 ? TINYMPC_KERNEL_GPI : TINYMPC_KERNEL_TPI);
+    s->stats.kernel_family = family;
     s->stats.ctas = (int)ctas;
-    s->stats.gpi_instances = Bg;
+    s->stats.gpi_instances = family == TINYMPC_KERNEL_TPI ? 0 : io->B;
+    s->stats.workspace_bytes = (int64_t)ws_bytes;
     return TINYMPC_OK;
 }
 
@@ -432,7 +413,7 @@ int enqueue(tinympc_b200_solver *s, const tinympc_batch_t *io, cudaStream_t stre
 namespace {
 template <typename T>
 int precompute_batch_T(int nx, int nu, int64_t B, const T *A, const T *Bm, const T *f, const T *Qd, const T *Rd, const T *rho,
-                       T *out, int nthreads) {
+                       T *out, int nthreads, int64_t *bad_index = nullptr) {
     const int64_t M = tinympc_b200_model_blob_elems(nx, nu);
     nthreads = (int)std::max<int64_t>(1, std::min<int64_t>(nthreads, B));
     std::vector<int64_t> bad(nthreads, 0);
@@ -463,7 +444,13 @@ int precompute_batch_T(int nx, int nu, int64_t B, const T *A, const T *Bm, const
     int64_t first = 0;
     for (int64_t v : bad)
         if (v && (!first || v < first)) first = v;
-    return first ? -(int)first : 0;
+    if (first) {
+        fail(TINYMPC_ERR_SINGULAR, "singular R + B'PB in the Riccati recursion of instance " + std::to_string(first - 1));
+        if (bad_index) *bad_index = first - 1;
+        return TINYMPC_ERR_SINGULAR;
+    }
+    if (bad_index) *bad_index = -1;
+    return 0;
 }
 }  // namespace
 
@@ -556,10 +543,19 @@ int tinympc_b200_create(const tinympc_problem_t *p, int32_t device, tinympc_b200
     const tmpc::DimEntry *dim = find_dim(p->nx, p->nu);
     if (!dim) return fail(TINYMPC_ERR_UNSUPPORTED, "no kernel compiled for this (nx, nu); add it to TM_DIMS in csrc/launch.h");
     if (p->num_state_cones > 4 || p->num_input_cones > 4) return fail(TINYMPC_ERR_UNSUPPORTED, "at most 4 cones per side");
-    for (int c = 0; c < p->num_state_cones; ++c)
+    for (int c = 0; c < p->num_state_cones && p->Acx && p->qcx; ++c)
         if (p->qcx[c] != 3 || p->Acx[c] < 0 || p->Acx[c] + 3 > p->nx) return fail(TINYMPC_ERR_CONE_DIM, "state cone must be 3-dimensional and inside the state");
-    for (int c = 0; c < p->num_input_cones; ++c)
+    for (int c = 0; c < p->num_input_cones && p->Acu && p->qcu; ++c)
         if (p->qcu[c] != 3 || p->Acu[c] < 0 || p->Acu[c] + 3 > p->nu) return fail(TINYMPC_ERR_CONE_DIM, "input cone must be 3-dimensional and inside the input");
+
+    if (p->num_state_linear < 0 || p->num_input_linear < 0 || p->num_tv_state_linear < 0 || p->num_tv_input_linear < 0)
+        return fail(TINYMPC_ERR_ARG, "negative constraint count");
+    if ((p->num_state_linear > 0 && (!p->Alin_x || !p->blin_x)) || (p->num_input_linear > 0 && (!p->Alin_u || !p->blin_u)) ||
+        (p->num_tv_state_linear > 0 && (!p->tv_Alin_x || !p->tv_blin_x)) ||
+        (p->num_tv_input_linear > 0 && (!p->tv_Alin_u || !p->tv_blin_u)))
+        return fail(TINYMPC_ERR_ARG, "hyperplane count > 0 with a NULL normal matrix or offset vector");
+    if ((p->num_state_cones > 0 && (!p->Acx || !p->qcx || !p->cx)) || (p->num_input_cones > 0 && (!p->Acu || !p->qcu || !p->cu)))
+        return fail(TINYMPC_ERR_ARG, "cone count > 0 with a NULL index / mu vector");
 
     int ndev = 0;
     CUDA_TRY(cudaGetDeviceCount(&ndev));
@@ -613,13 +609,22 @@ int tinympc_b200_create(const tinympc_problem_t *p, int32_t device, tinympc_b200
     s->ncx = p->num_state_cones; s->ncu = p->num_input_cones;
     for (int c = 0; c < s->ncx; ++c) { s->cone_x_start[c] = p->Acx[c]; s->cone_x_mu[c] = rd(p->cx, c); }
     for (int c = 0; c < s->ncu; ++c) { s->cone_u_start[c] = p->Acu[c]; s->cone_u_mu[c] = rd(p->cu, c); }
+    // the reference applies the cones of a knot point one after the other (admm.cpp:115-121): overlapping cones see each
+    // other's result.  The lane-group kernels project them independently, which is the same thing iff they are disjoint.
+    for (int a = 0; a < s->ncx; ++a)
+        for (int b = a + 1; b < s->ncx; ++b)
+            if (std::abs(s->cone_x_start[a] - s->cone_x_start[b]) < 3) s->cones_disjoint = false;
+    for (int a = 0; a < s->ncu; ++a)
+        for (int b = a + 1; b < s->ncu; ++b)
+            if (std::abs(s->cone_u_start[a] - s->cone_u_start[b]) < 3) s->cones_disjoint = false;
     s->nlx = p->num_state_linear; s->nlu = p->num_input_linear;
     if (s->nlx > 0) ok &= !upload(s->d_Alin_x, p->Alin_x, es * s->nlx * nx) && !upload(s->d_blin_x, p->blin_x, es * s->nlx);
     if (s->nlu > 0) ok &= !upload(s->d_Alin_u, p->Alin_u, es * s->nlu * nu) && !upload(s->d_blin_u, p->blin_u, es * s->nlu);
     s->ntvx = p->num_tv_state_linear; s->ntvu = p->num_tv_input_linear;
     if (s->ntvx > 0) ok &= !upload(s->d_tvA_x, p->tv_Alin_x, es * s->ntvx * N * nx) && !upload(s->d_tvb_x, p->tv_blin_x, es * s->ntvx * N);
     if (s->ntvu > 0) ok &= !upload(s->d_tvA_u, p->tv_Alin_u, es * s->ntvu * (N - 1) * nu) && !upload(s->d_tvb_u, p->tv_blin_u, es * s->ntvu * (N - 1));
-    ok &= cudaEventCreate(&s->ev0) == cudaSuccess && cudaEventCreate(&s->ev1) == cudaSuccess;
+    ok &= cudaEventCreate(&s->ev0) == cudaSuccess && cudaEventCreate(&s->ev1) == cudaSuccess &&
+          cudaEventCreateWithFlags(&s->ev_last, cudaEventDisableTiming) == cudaSuccess;
     if (!ok) {
         tinympc_b200_destroy(s);
         return fail(TINYMPC_ERR_CUDA, std::string("problem upload failed: ") + cudaGetErrorString(cudaGetLastError()));
@@ -633,7 +638,8 @@ int tinympc_b200_destroy(tinympc_b200_solver_t *s) {
     if (!s) return TINYMPC_OK;
     cudaSetDevice(s->device);
     DevBuf *bufs[] = {&s->d_xmin, &s->d_xmax, &s->d_umin, &s->d_umax, &s->d_Alin_x, &s->d_blin_x, &s->d_Alin_u,
-                      &s->d_blin_u, &s->d_tvA_x, &s->d_tvb_x, &s->d_tvA_u, &s->d_tvb_u, &s->ws, &s->queue, &s->d_blob, &s->vscratch};
+                      &s->d_blin_u, &s->d_tvA_x, &s->d_tvb_x, &s->d_tvA_u, &s->d_tvb_u, &s->ws, &s->queue, &s->d_blob, &s->vscratch,
+                      &s->gps_ws, &s->shared_ref};
     for (DevBuf *b : bufs) b->release();
     for (int i = 0; i < tinympc_b200_solver::SLOTS; ++i) {
         s->dio[i].release();
@@ -646,11 +652,7 @@ int tinympc_b200_destroy(tinympc_b200_solver_t *s) {
     if (s->st_h2d) cudaStreamDestroy(s->st_h2d);
     if (s->st_k) cudaStreamDestroy(s->st_k);
     if (s->st_d2h) cudaStreamDestroy(s->st_d2h);
-    if (s->st_a) cudaStreamDestroy(s->st_a);
-    if (s->st_b) cudaStreamDestroy(s->st_b);
-    if (s->ev_fork) cudaEventDestroy(s->ev_fork);
-    if (s->ev_ja) cudaEventDestroy(s->ev_ja);
-    if (s->ev_jb) cudaEventDestroy(s->ev_jb);
+    if (s->ev_last) cudaEventDestroy(s->ev_last);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     delete s;
@@ -673,7 +675,8 @@ int tinympc_b200_get_settings(const tinympc_b200_solver_t *s, tinympc_settings_t
 int tinympc_b200_set_mode(tinympc_b200_solver_t *s, int32_t mode, int32_t family) {
     if (!s) return fail(TINYMPC_ERR_ARG, "null solver");
     if (mode != TINYMPC_MODE_STRICT && mode != TINYMPC_MODE_FAST) return fail(TINYMPC_ERR_ARG, "bad mode");
-    if (family < TINYMPC_KERNEL_AUTO || family > TINYMPC_KERNEL_HYBRID) return fail(TINYMPC_ERR_ARG, "bad kernel family");
+    if (family != TINYMPC_KERNEL_AUTO && family != TINYMPC_KERNEL_TPI && family != TINYMPC_KERNEL_GPI && family != TINYMPC_KERNEL_GPS)
+        return fail(TINYMPC_ERR_ARG, "bad kernel family");
     s->mode = mode;
     s->family = family;
     return TINYMPC_OK;
@@ -766,8 +769,8 @@ int tinympc_b200_solve_host(tinympc_b200_solver_t *s, const tinympc_batch_t *io)
         }
     }
 
-    // shared (not per-instance) references are uploaded once
-    DevBuf shared_ref;
+    // shared (not per-instance) references are uploaded once, into a buffer the handle keeps
+    DevBuf &shared_ref = s->shared_ref;
     tinympc_batch_t dev = *io;  // template for the device-side descriptor
     const bool cold = io->cold_start != 0;
     std::vector<Field> fields;
@@ -778,6 +781,7 @@ int tinympc_b200_solve_host(tinympc_b200_solver_t *s, const tinympc_batch_t *io)
     {
         size_t need = (io->xref_per_instance ? 0 : bx) + ((io->Uref && !io->uref_per_instance) ? bu : 0);
         if (need) {
+            if (need + 256 > shared_ref.bytes && s->have_last) CUDA_TRY(cudaEventSynchronize(s->ev_last));  // about to reallocate
             if (shared_ref.ensure(need + 256)) return fail(TINYMPC_ERR_CUDA, "shared reference allocation failed");
             char *c = (char *)shared_ref.p;
             if (!io->xref_per_instance) {
@@ -920,7 +924,6 @@ int tinympc_b200_solve_host(tinympc_b200_solver_t *s, const tinympc_batch_t *io)
     for (int i = 0; i < SLOTS; ++i)
         if (drain(i)) return fail(TINYMPC_ERR_CUDA, "event sync failed");
     CUDA_TRY(cudaStreamSynchronize(s->st_h2d));
-    shared_ref.release();
     s->stats.instances = B;
     s->stats.kernel_launches = launches;
     s->timed = false;

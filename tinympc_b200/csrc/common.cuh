@@ -197,6 +197,20 @@ __device__ __forceinline__ void project_soc3(T &s0, T &s1, T &s2, T mu_T) {
 
 constexpr int MAX_CONES = 4;  // cones per knot point and per side held in the parameter block
 
+// Record layout of the streamed lane-group kernel (gps_kernel.cuh): element offsets of every field inside the
+// per-warp, per-knot-point record [field][instance of the warp][row]; -1 = field absent.  Family index: 0 = cones,
+// 1 = static hyperplanes, 2 = time-varying hyperplanes.
+struct GpsLayout {
+    int d;                        // d_k                                  (written backward, read forward)
+    int vnew, g, gf[3];           // box slack (doubles as work->v), box dual, family duals      (state-shaped)
+    int znew, y, yf[3];           //                                                              (input-shaped)
+    int q, r;                     // linear cost of the NEXT iteration    (written forward, read backward)
+    int vprev, zprev;             // previous box slacks, only when work->v / work->z are persisted
+    int vf[3], zf[3];             // family slacks, only when the caller asks for them back
+    int rec;                      // elements per record (a multiple of 16 bytes)
+    int dist;                     // prefetch distance of the cp.async ring (stages = dist + 1)
+};
+
 // Kernel parameter block.  Passed by value (__grid_constant__): it lives in the constant bank, so with
 // compile-time indices the matrix entries become immediate constant operands of the FMA instructions.
 // All matrices are column-major copies of the reference's cache / workspace (types.hpp:43-51,186-190).
@@ -247,6 +261,8 @@ struct KParams {
     T *u0;  // [B][nu] first rollout input, may be null
     const T *models;  // GPI: per-instance cache blobs [B][blob+1] (A,B,f,Qd,Rd,Kinf,Pinf,Quu,AmBKt,APf,BPf,rho) or null
     T *gpi_vscratch;  // GPI: [B][N][L][PVP] copy of the previous primal pack (work->v / work->z) while v,z are persisted
+    T *gps_ws;        // GPS: [resident warps][N][gps.rec] streamed state records
+    GpsLayout gps;
     // TPI workspace (structure-of-arrays, 16-byte vectors, [k][vec][Bpad])
     void *w_v[2], *w_z[2], *w_g, *w_y, *w_d;
     void *w_vc, *w_zc, *w_gc, *w_yc, *w_vl, *w_zl, *w_gl, *w_yl, *w_vlt, *w_zlt, *w_glt, *w_ylt;

@@ -11,7 +11,7 @@ namespace tmpc {
 struct LaunchDesc {
     int dtype;   // TINYMPC_F32 / F64
     int fast;    // TINYMPC_MODE_FAST ?
-    int family;  // TINYMPC_KERNEL_TPI / GPI (resolved, never AUTO)
+    int family;  // TINYMPC_KERNEL_TPI / GPI / GPS (resolved, never AUTO)
     int ext;     // any of soc / linear / tv-linear enabled
 
     // host copies of the model + cache in the native dtype (column-major)
@@ -37,6 +37,8 @@ struct LaunchDesc {
     const void *h_xlo, *h_xhi, *h_ulo, *h_uhi;  // host copies of column 0 of the bounds (native dtype), may be null
     void *work_queue;  // GPI: device int64 counter (zeroed by the caller)
     void *gpi_vscratch;  // GPI: scratch for work->v / work->z persistence (allocated by the caller when state.v/z given)
+    void *gps_ws;        // GPS: streamed state records of the resident slots (allocated by the caller, see out_ws_need)
+    size_t gps_ws_bytes;
 
     cudaStream_t stream;
     int sm_count;
@@ -44,7 +46,11 @@ struct LaunchDesc {
 
     // filled by the launcher
     int out_threads, out_ctas, out_smem, out_lanes_per_instance, out_instances_per_cta, out_tmem_cols;
+    size_t out_ws_need;  // GPS: workspace bytes this launch needs (set when the launcher returns TM_ERR_WORKSPACE)
 };
+
+// internal: the launcher needs a larger gps_ws (size in out_ws_need); never leaves the library
+constexpr int TM_ERR_WORKSPACE = -100;
 
 // per-(nx,nu) entry: returns 0 on success, TINYMPC_ERR_UNSUPPORTED when (dtype,family,...) is not compiled
 typedef int (*launch_fn)(LaunchDesc *);
@@ -59,6 +65,8 @@ struct DimEntry {
     // batched cache precompute on the device (precompute_kernel.cuh): device pointers, one model blob per instance
     int (*precompute_batch)(int dtype, int64_t B, const void *A, const void *Bm, const void *f, const void *Qdiag, const void *Rdiag,
                             const void *rho, void *models_out, int32_t *sweeps_out, int sm_count, cudaStream_t stream);
+    // streamed lane-group kernel (gps_kernel.cuh): lanes per instance for this dtype, 0 = shape not available
+    int (*gps_lanes)(int dtype);
 };
 
 }  // namespace tmpc

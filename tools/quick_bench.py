@@ -22,7 +22,7 @@ ap.add_argument("--B", type=int, default=0)
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--max_iter", type=int, default=0)
 a = ap.parse_args()
-K = dict(auto=abi.KERNEL_AUTO, tpi=abi.KERNEL_TPI, gpi=abi.KERNEL_GPI, hybrid=abi.KERNEL_HYBRID)[a.kernel]
+K = dict(auto=abi.KERNEL_AUTO, tpi=abi.KERNEL_TPI, gpi=abi.KERNEL_GPI, gps=abi.KERNEL_GPS)[a.kernel]
 M = dict(strict=abi.MODE_STRICT, fast=abi.MODE_FAST)[a.mode]
 if a.config == "c2":
     spec, dt, B = wl.quadrotor(N=50), np.float32, a.B or 65536
@@ -50,4 +50,4 @@ iters = int(out["iter"].sum().item())
 best = min(ms[2:] or ms)
 print(f"{a.config} kernel={a.kernel}->{st['kernel_family']} mode={a.mode} B={B} iters={iters} solved={int(out['solved'].sum().item())} "
       f"ms(all)={[round(m, 3) for m in ms]} best={best:.3f} ms  -> {B / best * 1e3:.3e} inst/s  {iters / best * 1e3:.3e} ADMM it/s "
-      f"gpiB={st['gpi_instances']} ctas={st['ctas']} thr={st['threads_per_cta']} smem={st['smem_bytes_per_cta']} L={st['lanes_per_instance']}")
+      f"ws={st["workspace_bytes"] >> 20}MiB gpiB={st['gpi_instances']} ctas={st['ctas']} thr={st['threads_per_cta']} smem={st['smem_bytes_per_cta']} L={st['lanes_per_instance']}")

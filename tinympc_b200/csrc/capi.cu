@@ -132,7 +132,6 @@ struct tinympc_b200_solver {
     tinympc_settings_t settings;
     int mode = TINYMPC_MODE_STRICT;
     int family = TINYMPC_KERNEL_AUTO;
-    bool cones_disjoint = true;  // the lane-group kernels project the cones of a knot point independently
     // workspace (one solve at a time per handle: enqueue() serialises launches issued on different streams)
     DevBuf ws;
     DevBuf queue;
@@ -200,7 +199,7 @@ int resolve_family(const tinympc_b200_solver *s, const Features &ft, int *smem_o
         gpi_ok = smem > 0;
     }
     if (smem_out) *smem_out = smem;
-    const bool gps_ok = s->dim->gps_lanes && s->dim->gps_lanes(s->dtype) > 0 && (!(ft.soc_x || ft.soc_u) || s->cones_disjoint);
+    const bool gps_ok = s->dim->gps_lanes && s->dim->gps_lanes(s->dtype) > 0;
     if (s->family == TINYMPC_KERNEL_GPI) return gpi_ok ? TINYMPC_KERNEL_GPI : (gps_ok ? TINYMPC_KERNEL_GPS : -1);
     if (s->family == TINYMPC_KERNEL_GPS) return gps_ok ? TINYMPC_KERNEL_GPS : -1;
     if (s->family == TINYMPC_KERNEL_TPI) return TINYMPC_KERNEL_TPI;
@@ -333,7 +332,7 @@ int enqueue(tinympc_b200_solver *s, const tinympc_batch_t *io, cudaStream_t stre
             return fail(TINYMPC_ERR_UNSUPPORTED, "per-instance models need the on-chip GPI kernel (box constraints, horizon fitting in shared memory)");
         family = TINYMPC_KERNEL_GPI;
     }
-    if (family < 0) return fail(TINYMPC_ERR_UNSUPPORTED, "the requested lane-group kernel does not cover this problem (shape, or overlapping cones)");
+    if (family < 0) return fail(TINYMPC_ERR_UNSUPPORTED, "the requested lane-group kernel does not cover this problem shape");
     // The launch scratch of a handle (work queue, workspaces, timing events) is single-buffered: a solve enqueued on a
     // different stream than the previous one first waits for it.
     if (s->have_last && s->last_stream != stream) CUDA_TRY(cudaStreamWaitEvent(stream, s->ev_last, 0));
@@ -609,14 +608,6 @@ int tinympc_b200_create(const tinympc_problem_t *p, int32_t device, tinympc_b200
     s->ncx = p->num_state_cones; s->ncu = p->num_input_cones;
     for (int c = 0; c < s->ncx; ++c) { s->cone_x_start[c] = p->Acx[c]; s->cone_x_mu[c] = rd(p->cx, c); }
     for (int c = 0; c < s->ncu; ++c) { s->cone_u_start[c] = p->Acu[c]; s->cone_u_mu[c] = rd(p->cu, c); }
-    // the reference applies the cones of a knot point one after the other (admm.cpp:115-121): overlapping cones see each
-    // other's result.  The lane-group kernels project them independently, which is the same thing iff they are disjoint.
-    for (int a = 0; a < s->ncx; ++a)
-        for (int b = a + 1; b < s->ncx; ++b)
-            if (std::abs(s->cone_x_start[a] - s->cone_x_start[b]) < 3) s->cones_disjoint = false;
-    for (int a = 0; a < s->ncu; ++a)
-        for (int b = a + 1; b < s->ncu; ++b)
-            if (std::abs(s->cone_u_start[a] - s->cone_u_start[b]) < 3) s->cones_disjoint = false;
     s->nlx = p->num_state_linear; s->nlu = p->num_input_linear;
     if (s->nlx > 0) ok &= !upload(s->d_Alin_x, p->Alin_x, es * s->nlx * nx) && !upload(s->d_blin_x, p->blin_x, es * s->nlx);
     if (s->nlu > 0) ok &= !upload(s->d_Alin_u, p->Alin_u, es * s->nlu * nu) && !upload(s->d_blin_u, p->blin_u, es * s->nlu);

@@ -195,20 +195,31 @@ __device__ __forceinline__ void project_soc3(T &s0, T &s1, T &s2, T mu_T) {
     }
 }
 
+// branch-free twin of project_soc3 (same operations, same results): every lane of a warp projects a different cone, so
+// the three cases are computed and selected instead of branched on
+template <typename T>
+__device__ __forceinline__ void project_soc3_sel(T &s0, T &s1, T &s2, T mu_T) {
+    const float mu = (float)mu_T;
+    const T u0 = s2 * (T)mu;
+    T sq = s0 * s0;
+    sq = sq + s1 * s1;
+    const float a = (float)tsqrt(sq);
+    const T ad = (T)a;
+    const bool below = ad <= -u0, inside = ad <= u0;
+    const T third = (T)(a / mu);
+    const T c = T(0.5) * (T(1) + u0 / ad);
+    const T r0 = c * s0, r1 = c * s1, r2 = c * third;
+    s0 = below ? T(0) : (inside ? s0 : r0);
+    s1 = below ? T(0) : (inside ? s1 : r1);
+    s2 = below ? T(0) : (inside ? s2 : r2);
+}
+
 constexpr int MAX_CONES = 4;  // cones per knot point and per side held in the parameter block
 
-// Record layout of the streamed lane-group kernel (gps_kernel.cuh): element offsets of every field inside the
-// per-warp, per-knot-point record [field][instance of the warp][row]; -1 = field absent.  Family index: 0 = cones,
-// 1 = static hyperplanes, 2 = time-varying hyperplanes.
+// Run-time part of the streamed lane-group kernel's workspace description (gps_kernel.cuh); the record layout itself is a
+// compile-time function of the shape and of the compiled-in constraint families (GpsRec).
 struct GpsLayout {
-    int d;                        // d_k                                  (written backward, read forward)
-    int vnew, g, gf[3];           // box slack (doubles as work->v), box dual, family duals      (state-shaped)
-    int znew, y, yf[3];           //                                                              (input-shaped)
-    int q, r;                     // linear cost of the NEXT iteration    (written forward, read backward)
-    int vprev, zprev;             // previous box slacks, only when work->v / work->z are persisted
-    int vf[3], zf[3];             // family slacks, only when the caller asks for them back
-    int rec;                      // elements per record (a multiple of 16 bytes)
-    int dist;                     // prefetch distance of the cp.async ring (stages = dist + 1)
+    int has_b;  // the optional-output region (previous box slacks, family slacks) is allocated and maintained
 };
 
 // Kernel parameter block.  Passed by value (__grid_constant__): it lives in the constant bank, so with

@@ -1,22 +1,31 @@
 // gps_kernel.cuh — lane-group-per-instance batched ADMM solve with the N-indexed state STREAMED through a per-slot
 // workspace in global memory (L2 / HBM) behind a cp.async ring in shared memory ("GPS").
 //
-// Same lane mapping as the on-chip kernel (gpi_kernel.cuh): L lanes own one MPC instance, lane l owns the state rows
+// Same lane mapping as the on-chip kernel (gpi_kernel.cuh): L lanes form a group, lane l owns the state rows
 // [l*RX, (l+1)*RX) and the input rows [l*RU, (l+1)*RU); its rows of AmBKt / B^T / A / Kinf / Kinf^T / B / Quu_inv live
 // in registers (staged once per CTA by a TMA bulk copy), every mat-vec is RX+RU ascending-k dot products per lane and
 // the fresh vector is all-gathered inside the lane group through shared memory.  What differs:
 //   * every constraint family of the reference is covered: box (admm.cpp:85-98), second-order cones (project_soc,
 //     admm.cpp:39-60,102-135), static and time-varying hyperplanes (admm.cpp:70-73,138-211) with their cost / dual
-//     twins (admm.cpp:228-255,268-303), in fp32 and fp64;
+//     twins (admm.cpp:228-255,268-303), in fp32 and fp64.  FAM (template) = bit mask of the families compiled in
+//     (1 cones, 2 static hyperplanes, 4 time-varying hyperplanes);
+//   * a lane group runs NI (1 or 2) instances at once on the SAME matrix registers: two independent dependency chains
+//     per thread.  The sweeps are recurrences of dependent fp64 / fp32 operations and registers cap the kernel at 8
+//     warps per SM, so instruction-level parallelism is what hides the arithmetic latency (ncu, rocket landing fp64 with
+//     one instance per group: 1.8 `wait` stalls per issued instruction, issue slots 39 % busy);
 //   * the per-instance state does not have to fit on chip (rocket landing, N = 100, fp64: 31 KB per instance): it lives
 //     in a workspace indexed by RESIDENT SLOT (not by instance), one record per (warp, knot point) laid out
-//     [field][instance of the warp][row], so that every field access of a warp is one contiguous run of bytes.  Each
+//     [field][slot of the warp][row], so that every field access of a warp is one contiguous run of bytes.  Each
 //     lane moves only its own rows: cp.async (4/8/16-byte chunks) into a private slice of a shared-memory ring
 //     `dist` steps ahead of their use, plain vector stores on the way out.  A lane only ever re-reads what it wrote
 //     itself, so program order is all the ordering the ring needs (no barriers, no drain at the sweep turnarounds);
 //   * the linear cost of the NEXT iteration (q_k, r_k, p_{N-1}; update_linear_cost, admm.cpp:262-304) is evaluated
 //     in the forward sweep, where the fresh slack / dual values are in registers, and stored: the backward sweep
-//     reads q, r (nx+nu values per knot point) instead of every slack / dual pair (up to 8 (nx+nu)).
+//     reads q, r (nx+nu values per knot point) instead of every slack / dual pair (up to 8 (nx+nu));
+//   * the cone projections of a knot point (state and input cones of the NI instances of a group) are work items spread
+//     over the lanes of the group — every lane projects a different cone (branch-free project_soc) instead of all L
+//     lanes repeating the same one — and are applied one after the other through shared memory, exactly like the
+//     reference's in-place loop (admm.cpp:115-121), so overlapping cones are fine.
 // The kernel is persistent (one CTA per SM); slots are refilled from a global atomic queue as instances terminate
 // (per-instance termination, admm.cpp:310-328).  Reference semantics: tiny_solve -> solve (admm.cpp:331-455).
 #pragma once
@@ -25,41 +34,71 @@
 
 namespace tmpc {
 
-constexpr int gps_gcd(int a, int b) { return b == 0 ? a : gps_gcd(b, a % b); }
+__host__ __device__ constexpr int gps_gcd(int a, int b) { return b == 0 ? a : gps_gcd(b, a % b); }
+__host__ __device__ constexpr int gps_popc(int m) { return (m & 1) + ((m >> 1) & 1) + ((m >> 2) & 1); }
 
-template <int NX, int NU, int L, int ES, bool EXT>
+template <int NX, int NU, int L, int ES, int NI, int FAM>
 struct GpsCfg {
     static constexpr int RX = (NX + L - 1) / L;
     static constexpr int RU = (NU + L - 1) / L;
-    static constexpr int IPW = 32 / L;
+    static constexpr int IPW = 32 / L;    // lane groups per warp
+    static constexpr int SPW = IPW * NI;  // instances (slots) per warp; slot index = j * IPW + group
     static constexpr int W = 16 / ES;
     static constexpr int NXP = (L * RX + W - 1) / W * W;
     static constexpr int NUP = (L * RU + W - 1) / W * W;
-    static constexpr int GBUF = IPW * (NXP > NUP ? NXP : NUP);
+    static constexpr int GBX = SPW * NXP, GBU = SPW * NUP;  // gather scratch (elements): state vectors, input vectors
     // chunk sizes (bytes) of a lane's piece: global side (limited by the row pitch of an instance) and shared side
     static constexpr int CX = gps_gcd(16, gps_gcd(NX * ES, RX * ES));
     static constexpr int CU = gps_gcd(16, gps_gcd(NU * ES, RU * ES));
     static constexpr int SX = gps_gcd(16, RX * ES);
     static constexpr int SU = gps_gcd(16, RU * ES);
-    // ring piece slots.  state-shaped: 0 vnew (backward: q), 1 g, 2 xref, 3.. family duals
+    // ring piece slots.  state-shaped: 0 vnew (backward: q), 1 g, 2 xref, 3.. family duals (compiled-in families only)
     //                    input-shaped: 0 d (backward: r), 1 znew, 2 y, 3 uref, 4.. family duals
-    static constexpr int XP = EXT ? 6 : 3;
-    static constexpr int UP = EXT ? 7 : 4;
-    static constexpr int PXB = 32 * RX * ES;  // bytes of one state-shaped piece slot (32 lanes)
+    static constexpr int NF = gps_popc(FAM);
+    static constexpr int XP = 3 + NF;
+    static constexpr int UP = 4 + NF;
+    static constexpr int PXB = 32 * RX * ES;  // bytes of one state-shaped piece slot (32 lanes, one instance of the group)
     static constexpr int PUB = 32 * RU * ES;
-    static constexpr int STAGE_BYTES = XP * PXB + UP * PUB;
+    static constexpr int STAGE_BYTES = NI * (XP * PXB + UP * PUB);
     static constexpr int MAT_REGS = RX * (2 * NX + 2 * NU + 3) + RU * (2 * NX + NU + 2);
     static constexpr bool ok = (NX % RX == 0) && (NU % RU == 0) && (MAT_REGS * (ES / 4) <= 150);
-    __host__ __device__ static constexpr size_t warp_bytes(int stages) { return (size_t)GBUF * ES + (size_t)stages * STAGE_BYTES; }
+    static constexpr size_t WARP_BYTES = (size_t)(GBX + GBU) * ES + (size_t)3 * STAGE_BYTES;  // 3 = GPS_STAGES
+    // ring slot of family f's dual (f must be compiled in)
+    __host__ __device__ static constexpr int fslot(int f) { return gps_popc(FAM & ((1 << f) - 1)); }
 };
+
+// Record layout: one record per (warp, knot point), every field [slot of the warp][row] padded to 16 bytes.  Region A is
+// what the sweeps stream; region B (previous box slacks for work->v / work->z, family slacks) exists only when the caller
+// wants those arrays back.  All offsets are compile-time, so that every access is [running pointer + immediate].
+template <int NX, int NU, int SPW, int ES, int FAM>
+struct GpsRec {
+    __host__ __device__ static constexpr int fe(int rows) { return (SPW * rows * ES + 15) / 16 * 16 / ES; }  // elements of one field
+    static constexpr int FXE = fe(NX), FUE = fe(NU), NF = gps_popc(FAM);
+    __host__ __device__ static constexpr int fslot(int f) { return gps_popc(FAM & ((1 << f) - 1)); }
+    static constexpr int d = 0, vnew = d + FUE, g = vnew + FXE, gf0 = g + FXE, znew = gf0 + NF * FXE, y = znew + FUE,
+                         yf0 = y + FUE, q = yf0 + NF * FUE, r = q + FXE, recA = r + FUE;
+    __host__ __device__ static constexpr int gf(int f) { return gf0 + fslot(f) * FXE; }
+    __host__ __device__ static constexpr int yf(int f) { return yf0 + fslot(f) * FUE; }
+    static constexpr int vprev = 0, zprev = vprev + FXE, vf0 = zprev + FUE, zf0 = vf0 + NF * FXE, recB = zf0 + NF * FUE;
+    __host__ __device__ static constexpr int vf(int f) { return vf0 + fslot(f) * FXE; }
+    __host__ __device__ static constexpr int zf(int f) { return zf0 + fslot(f) * FUE; }
+};
+
+constexpr int GPS_DIST = 2;              // prefetch distance of the cp.async ring (sweep steps)
+constexpr int GPS_STAGES = GPS_DIST + 1;
 
 // smallest lane-group width whose matrix rows fit in registers (0 = none)
 template <typename T, int NX, int NU>
 constexpr int gps_pick_L() {
-    if (GpsCfg<NX, NU, 4, (int)sizeof(T), true>::ok) return 4;
-    if (GpsCfg<NX, NU, 8, (int)sizeof(T), true>::ok) return 8;
-    if (GpsCfg<NX, NU, 16, (int)sizeof(T), true>::ok) return 16;
+    if (GpsCfg<NX, NU, 4, (int)sizeof(T), 1, 0>::ok) return 4;
+    if (GpsCfg<NX, NU, 8, (int)sizeof(T), 1, 0>::ok) return 8;
+    if (GpsCfg<NX, NU, 16, (int)sizeof(T), 1, 0>::ok) return 16;
     return 0;
+}
+// instances per lane group: two when the matrix rows leave room for a second set of working registers
+template <typename T, int NX, int NU, int L>
+constexpr int gps_pick_NI() {
+    return GpsCfg<NX, NU, L, (int)sizeof(T), 1, 0>::MAT_REGS * (int)(sizeof(T) / 4) <= 128 ? 2 : 1;
 }
 
 constexpr int GPS_MAX_WARPS = 8;
@@ -98,6 +137,13 @@ __device__ __forceinline__ void lds_chunk(unsigned a, float (&v)[2]) {
 __device__ __forceinline__ void lds_chunk(unsigned a, float (&v)[4]) { ldsv(a, v); }
 __device__ __forceinline__ void lds_chunk(unsigned a, double (&v)[1]) { v[0] = lds(a, 0.0); }
 __device__ __forceinline__ void lds_chunk(unsigned a, double (&v)[2]) { ldsv(a, v); }
+__device__ __forceinline__ void sts_chunk(unsigned a, const float (&v)[1]) { sts(a, v[0]); }
+__device__ __forceinline__ void sts_chunk(unsigned a, const float (&v)[2]) {
+    asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(a), "f"(v[0]), "f"(v[1]) : "memory");
+}
+__device__ __forceinline__ void sts_chunk(unsigned a, const float (&v)[4]) { stsv(a, v); }
+__device__ __forceinline__ void sts_chunk(unsigned a, const double (&v)[1]) { sts(a, v[0]); }
+__device__ __forceinline__ void sts_chunk(unsigned a, const double (&v)[2]) { stsv(a, v); }
 __device__ __forceinline__ void stg_chunk(float *p, const float (&v)[1]) { *p = v[0]; }
 __device__ __forceinline__ void stg_chunk(float *p, const float (&v)[2]) { *reinterpret_cast<float2 *>(p) = make_float2(v[0], v[1]); }
 __device__ __forceinline__ void stg_chunk(float *p, const float (&v)[4]) { *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]); }
@@ -116,6 +162,17 @@ __device__ __forceinline__ void lds_piece(unsigned a, T (&v)[R]) {
     }
 }
 template <typename T, int R, int CB>
+__device__ __forceinline__ void sts_piece(unsigned a, const T (&v)[R]) {
+    constexpr int E = CB / (int)sizeof(T);
+#pragma unroll
+    for (int c = 0; c < R / E; ++c) {
+        T t[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) t[e] = v[c * E + e];
+        sts_chunk(a + (unsigned)(c * CB), t);
+    }
+}
+template <typename T, int R, int CB>
 __device__ __forceinline__ void stg_piece(T *p, const T (&v)[R]) {
     constexpr int E = CB / (int)sizeof(T);
 #pragma unroll
@@ -125,11 +182,6 @@ __device__ __forceinline__ void stg_piece(T *p, const T (&v)[R]) {
         for (int e = 0; e < E; ++e) t[e] = v[c * E + e];
         stg_chunk(p + c * E, t);
     }
-}
-template <typename T, int R, int CB>
-__device__ __forceinline__ void ldg_piece(const T *p, T (&v)[R]) {  // plain global loads of a piece (write-back paths)
-#pragma unroll
-    for (int e = 0; e < R; ++e) v[e] = p[e];
 }
 
 // own rows of a vector every lane of the group holds in full: out[a] = full[l*R + a] without dynamic register indexing
@@ -145,22 +197,29 @@ __device__ __forceinline__ void extract_own(const T (&full)[NE], int l, T (&out)
     }
 }
 
-template <typename T, int NX, int NU, int L, bool FAST, bool EXT>
+template <int J>
+struct IdxTag {
+    static constexpr int value = J;
+};
+
+template <typename T, int NX, int NU, int L, int NI, int FAM, bool FAST>
 __global__ void __launch_bounds__(GPS_MAX_WARPS * 32, 1)
     gps_solve_kernel(const __grid_constant__ KParams<T, NX, NU> P, const T *__restrict__ gmat, unsigned long long *queue) {
-    using Cfg = GpsCfg<NX, NU, L, (int)sizeof(T), EXT>;
-    constexpr int RX = Cfg::RX, RU = Cfg::RU, W = Cfg::W, NXP = Cfg::NXP, NUP = Cfg::NUP;
+    using Cfg = GpsCfg<NX, NU, L, (int)sizeof(T), NI, FAM>;
+    using REC = GpsRec<NX, NU, Cfg::SPW, (int)sizeof(T), FAM>;
+    constexpr int RX = Cfg::RX, RU = Cfg::RU, IPW = Cfg::IPW, W = Cfg::W, NXP = Cfg::NXP, NUP = Cfg::NUP;
+    constexpr int D = GPS_DIST, S = GPS_STAGES, recA = REC::recA, recB = REC::recB;
+    constexpr int JX = IPW * NX, JU = IPW * NU;  // element distance between the two instances of a group inside a field
     constexpr int CX = Cfg::CX, CU = Cfg::CU, SX = Cfg::SX, SU = Cfg::SU;
     constexpr unsigned ES = (unsigned)sizeof(T);
-    constexpr unsigned PXB = Cfg::PXB, PUB = Cfg::PUB, STAGE = Cfg::STAGE_BYTES, XPB = Cfg::XP * Cfg::PXB;
+    constexpr unsigned PXB = Cfg::PXB, PUB = Cfg::PUB, STAGE = Cfg::STAGE_BYTES, XPB = NI * Cfg::XP * Cfg::PXB;
+    constexpr bool EXT = FAM != 0;
     static_assert(Cfg::ok, "lane mapping not available for this shape");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = P.N;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const int l = lane % L, slot = lane / L;
-    const GpsLayout &LY = P.gps;
-    const int D = LY.dist, S = D + 1;
-    const int rec = LY.rec;
+    const int l = lane % L, grp = lane / L;
+    const bool has_b = P.gps.has_b != 0;
     const T rho = P.rho;
 
     // ---- stage the cache blob into shared memory with one TMA bulk copy per CTA, pull this lane's rows into registers
@@ -232,50 +291,68 @@ __global__ void __launch_bounds__(GPS_MAX_WARPS * 32, 1)
     }
     __syncthreads();  // the staging area is reused below
 
-    // ---- shared memory of this warp: gather scratch + cp.async ring (S stages) ----
-    const unsigned wbytes = (unsigned)Cfg::warp_bytes(S);
-    const unsigned aGB = (unsigned)__cvta_generic_to_shared(smem_raw) + (unsigned)warp * wbytes;
-    const unsigned aRing = aGB + (unsigned)Cfg::GBUF * ES;
-    const unsigned aXl = aRing + (unsigned)lane * RX * ES;        // + stage*STAGE + piece*PXB
-    const unsigned aUl = aRing + XPB + (unsigned)lane * RU * ES;  // + stage*STAGE + piece*PUB
+    // ---- shared memory of this warp: gather scratch (state vectors | input vectors) + cp.async ring (S stages) ----
+    constexpr unsigned wbytes = (unsigned)Cfg::WARP_BYTES;
+    const unsigned aGX = (unsigned)__cvta_generic_to_shared(smem_raw) + (unsigned)warp * wbytes;
+    const unsigned aGU = aGX + (unsigned)Cfg::GBX * ES;
+    const unsigned aRing = aGU + (unsigned)Cfg::GBU * ES;
+    const unsigned aXl = aRing + (unsigned)lane * RX * ES;        // + stage offset + (piece*NI + j)*PXB
+    const unsigned aUl = aRing + XPB + (unsigned)lane * RU * ES;  // + stage offset + (piece*NI + j)*PUB
     // padding lanes never receive data: their ring slices stay zero
     for (unsigned o = (unsigned)lane * 16u; o < (unsigned)S * STAGE; o += 32u * 16u)
         asm volatile("st.shared.v4.f32 [%0], {%1,%1,%1,%1};" ::"r"(aRing + o), "f"(0.f) : "memory");
     __syncwarp();
+    // gather scratch of instance j of this lane's group (slot j*IPW + grp): own rows / whole vector
+    const unsigned gxf0 = aGX + (unsigned)(grp * NXP) * ES, gxo0 = gxf0 + (unsigned)(l * RX) * ES;
+    const unsigned guf0 = aGU + (unsigned)(grp * NUP) * ES, guo0 = guf0 + (unsigned)(l * RU) * ES;
+    auto gxo = [&](int j) { return gxo0 + (unsigned)(j * IPW * NXP) * ES; };
+    auto gxf = [&](int j) { return gxf0 + (unsigned)(j * IPW * NXP) * ES; };
+    auto guo = [&](int j) { return guo0 + (unsigned)(j * IPW * NUP) * ES; };
+    auto guf = [&](int j) { return guf0 + (unsigned)(j * IPW * NUP) * ES; };
 
-    auto gather_x = [&](const T (&own)[RX], T (&full)[NX]) {
+    auto gather_x = [&](const T (&own)[NI][RX], T (&full)[NI][NX]) {
         __syncwarp();
 #pragma unroll
-        for (int a = 0; a < RX; ++a) sts(aGB + (unsigned)(slot * NXP + l * RX + a) * ES, own[a]);
+        for (int j = 0; j < NI; ++j) sts_piece<T, RX, SX>(gxo(j), own[j]);
         __syncwarp();
 #pragma unroll
-        for (int c = 0; c < NXP / W; ++c) {
-            T t[W];
-            ldsv(aGB + (unsigned)(slot * NXP + c * W) * ES, t);
+        for (int j = 0; j < NI; ++j) {
 #pragma unroll
-            for (int e = 0; e < W; ++e)
-                if (c * W + e < NX) full[c * W + e] = t[e];
+            for (int c = 0; c < NXP / W; ++c) {
+                T t[W];
+                ldsv(gxf(j) + (unsigned)(c * W) * ES, t);
+#pragma unroll
+                for (int e = 0; e < W; ++e)
+                    if (c * W + e < NX) full[j][c * W + e] = t[e];
+            }
         }
     };
-    auto gather_u = [&](const T (&own)[RU], T (&full)[NU]) {
+    auto gather_u = [&](const T (&own)[NI][RU], T (&full)[NI][NU]) {
         __syncwarp();
 #pragma unroll
-        for (int b = 0; b < RU; ++b) sts(aGB + (unsigned)(slot * NUP + l * RU + b) * ES, own[b]);
+        for (int j = 0; j < NI; ++j) sts_piece<T, RU, SU>(guo(j), own[j]);
         __syncwarp();
 #pragma unroll
-        for (int c = 0; c < NUP / W; ++c) {
-            T t[W];
-            ldsv(aGB + (unsigned)(slot * NUP + c * W) * ES, t);
+        for (int j = 0; j < NI; ++j) {
 #pragma unroll
-            for (int e = 0; e < W; ++e)
-                if (c * W + e < NU) full[c * W + e] = t[e];
+            for (int c = 0; c < NUP / W; ++c) {
+                T t[W];
+                ldsv(guf(j) + (unsigned)(c * W) * ES, t);
+#pragma unroll
+                for (int e = 0; e < W; ++e)
+                    if (c * W + e < NU) full[j][c * W + e] = t[e];
+            }
         }
     };
 
-    // ---- streamed state of this warp: records [k][field][instance of the warp][row] ----
-    T *const wsw = P.gps_ws + (int64_t)(blockIdx.x * nwarps + warp) * N * rec;
-    T *const gx = wsw + slot * NX + l * RX;  // this lane's rows inside a state-shaped field of record 0
-    T *const gu = wsw + slot * NU + l * RU;
+    // ---- streamed state of this warp: records [k][field][slot of the warp][row] ----
+    // region A records first (N * recA), then, when maintained, the region B records (N * recB)
+    T *const wsw = P.gps_ws + (int64_t)(blockIdx.x * nwarps + warp) * N * (recA + (has_b ? recB : 0));
+    T *const wsb = wsw + (int64_t)N * recA;
+    // this lane's rows of the group's first instance inside a state-shaped / input-shaped field of record 0; the second
+    // instance of the group sits JX / JU elements further
+    T *const px0 = wsw + grp * NX + l * RX;
+    T *const pu0 = wsw + grp * NU + l * RU;
 
     const bool cold = P.cold != 0;
     const bool tvb = P.bounds_tv != 0;
@@ -292,146 +369,246 @@ __global__ void __launch_bounds__(GPS_MAX_WARPS * 32, 1)
         loU[b] = (enu && uvl) ? __ldg(P.u_min + l * RU + b) : -kInf;
         hiU[b] = (enu && uvl) ? __ldg(P.u_max + l * RU + b) : kInf;
     }
-    const bool keep_v = LY.vprev >= 0;
-    const bool fx[3] = {EXT && P.soc_x != 0, EXT && P.lin_x != 0, EXT && P.tvl_x != 0};
-    const bool fu[3] = {EXT && P.soc_u != 0, EXT && P.lin_u != 0, EXT && P.tvl_u != 0};
+    const bool keep_v = has_b && (P.s_v != nullptr || P.s_z != nullptr);
+    // family slacks are kept (region B) when the caller wants them back
+    const bool keep_f[3] = {has_b && (P.s_vcnew || P.s_zcnew), has_b && (P.s_vlnew || P.s_zlnew), has_b && (P.s_vlnew_tv || P.s_zlnew_tv)};
+    // a family takes part when it is compiled in AND enabled (warp-uniform)
+    const bool fx[3] = {(FAM & 1) && P.soc_x != 0, (FAM & 2) && P.lin_x != 0, (FAM & 4) && P.tvl_x != 0};
+    const bool fu[3] = {(FAM & 1) && P.soc_u != 0, (FAM & 2) && P.lin_u != 0, (FAM & 4) && P.tvl_u != 0};
     const bool has_uref = P.Uref != nullptr;
 
-    // ---- per-slot bookkeeping (identical in the L lanes of a slot) ----
-    int64_t inst = -1;
-    bool busy = false, want = true;
-    int it = 0, solved = 0;
-    T res_px = T(0), res_dx = T(0), res_pu = T(0), res_du = T(0);
-    T x0o[RX], pterm[RX];
+    // ---- per-slot bookkeeping (identical in the L lanes of a group) ----
+    int64_t inst[NI];
+    bool busy[NI], want[NI];
+    int it[NI], solved[NI];
+    T res_px[NI], res_dx[NI], res_pu[NI], res_du[NI];
+    T x0o[NI][RX], pterm[NI][RX];
+    const T *xrefp[NI], *urefp[NI];
 #pragma unroll
-    for (int a = 0; a < RX; ++a) x0o[a] = pterm[a] = T(0);
-    const T *xrefp = P.Xref + l * RX;
-    const T *urefp = has_uref ? P.Uref + l * RU : P.Xref;
+    for (int j = 0; j < NI; ++j) {
+        inst[j] = -1;
+        busy[j] = false;
+        want[j] = true;
+        it[j] = solved[j] = 0;
+        res_px[j] = res_dx[j] = res_pu[j] = res_du[j] = T(0);
+#pragma unroll
+        for (int a = 0; a < RX; ++a) x0o[j][a] = pterm[j][a] = T(0);
+        xrefp[j] = P.Xref + l * RX;
+        urefp[j] = has_uref ? P.Uref + l * RU : P.Xref;
+    }
 
-    // ---- projections of one gathered column (EXT) ----
-    // cones (admm.cpp:102-135): the lane group's vector is in the gather scratch; every lane projects each cone's
-    // three rows (project_soc, admm.cpp:39-60) and keeps the rows it owns.  Cones are pairwise disjoint (checked
-    // by the host; overlapping cones run on the thread-per-instance kernel).
-    auto cones_x = [&](T (&own)[RX]) {
+    // ---- cone projections of one knot point (admm.cpp:102-135).  The candidate slacks (x + gc, u + yc; own rows) of the
+    // group's NI instances go to the gather scratch; the 2*NI (instance, side) vectors are work items dealt to the
+    // lanes of the group; cone c of every item is projected in place (project_soc, admm.cpp:39-60), cone after cone as
+    // the reference's loop does; finally every lane reads its own rows back ----
+    auto cones_xu = [&](T (&sx)[NI][RX], T (&su)[NI][RU], const bool HASU) {
         __syncwarp();
 #pragma unroll
-        for (int a = 0; a < RX; ++a) sts(aGB + (unsigned)(slot * NXP + l * RX + a) * ES, own[a]);
-        __syncwarp();
-        for (int c = 0; c < P.ncx; ++c) {
-            const int st0 = P.cone_x_start[c];
-            T s0 = lds(aGB + (unsigned)(slot * NXP + st0) * ES, T()), s1 = lds(aGB + (unsigned)(slot * NXP + st0 + 1) * ES, T()),
-              s2 = lds(aGB + (unsigned)(slot * NXP + st0 + 2) * ES, T());
-            project_soc3(s0, s1, s2, P.cone_x_mu[c]);
-#pragma unroll
-            for (int a = 0; a < RX; ++a) {
-                const int i = l * RX + a;
-                own[a] = (i == st0) ? s0 : (i == st0 + 1) ? s1 : (i == st0 + 2) ? s2 : own[a];
-            }
+        for (int j = 0; j < NI; ++j) {
+            if (fx[0]) sts_piece<T, RX, SX>(gxo(j), sx[j]);
+            if (fu[0] && HASU) sts_piece<T, RU, SU>(guo(j), su[j]);
         }
-    };
-    auto cones_u = [&](T (&own)[RU]) {
         __syncwarp();
+        const int ncx = fx[0] ? P.ncx : 0, ncu = (fu[0] && HASU) ? P.ncu : 0;
+        const int nc = ncx > ncu ? ncx : ncu;
+        constexpr int ROUNDS = (2 * NI + L - 1) / L;
+        for (int c = 0; c < nc; ++c) {
 #pragma unroll
-        for (int b = 0; b < RU; ++b) sts(aGB + (unsigned)(slot * NUP + l * RU + b) * ES, own[b]);
-        __syncwarp();
-        for (int c = 0; c < P.ncu; ++c) {
-            const int st0 = P.cone_u_start[c];
-            T s0 = lds(aGB + (unsigned)(slot * NUP + st0) * ES, T()), s1 = lds(aGB + (unsigned)(slot * NUP + st0 + 1) * ES, T()),
-              s2 = lds(aGB + (unsigned)(slot * NUP + st0 + 2) * ES, T());
-            project_soc3(s0, s1, s2, P.cone_u_mu[c]);
-#pragma unroll
-            for (int b = 0; b < RU; ++b) {
-                const int j = l * RU + b;
-                own[b] = (j == st0) ? s0 : (j == st0 + 1) ? s1 : (j == st0 + 2) ? s2 : own[b];
+            for (int r = 0; r < ROUNDS; ++r) {
+                const int item = r * L + l, side = item & 1;
+                const int j_ = (item >> 1) < NI ? (item >> 1) : NI - 1;
+                const bool ok = item < 2 * NI && (side ? c < ncu : c < ncx);
+                const int st0 = ok ? (side ? P.cone_u_start[c] : P.cone_x_start[c]) : 0;
+                const T mu = side ? P.cone_u_mu[c] : P.cone_x_mu[c];
+                const unsigned base = (side ? guf(j_) : gxf(j_)) + (unsigned)st0 * ES;
+                T s0 = lds(base, T()), s1 = lds(base + ES, T()), s2 = lds(base + 2 * ES, T());
+                project_soc3_sel(s0, s1, s2, mu);
+                if (ok) {
+                    sts(base, s0);
+                    sts(base + ES, s1);
+                    sts(base + 2 * ES, s2);
+                }
             }
+            __syncwarp();
+        }
+#pragma unroll
+        for (int j = 0; j < NI; ++j) {
+            if (fx[0] && xvl) lds_piece<T, RX, SX>(gxo(j), sx[j]);
+            if (fu[0] && HASU && uvl) lds_piece<T, RU, SU>(guo(j), su[j]);
         }
     };
     // hyperplanes (admm.cpp:138-211): the rows are applied one after the other to the whole column, so every lane of
     // the group carries the full vector through the sequence (same arithmetic on every lane) and keeps its own rows
-    auto planes_x = [&](T (&own)[RX], const T *A, int ld, int row0, int n, const T *bvec) {
-        T full[NX];
+    auto planes_x = [&](T (&own)[NI][RX], const T *A, int ld, int row0, int n, const T *bvec) {
+        T full[NI][NX];
         gather_x(own, full);
-        project_rows<FAST, T, NX>(full, A, ld, row0, n, bvec);
-        T o[RX];
-        extract_own<T, NX, RX, L>(full, l, o);
 #pragma unroll
-        for (int a = 0; a < RX; ++a) own[a] = xvl ? o[a] : own[a];
+        for (int j = 0; j < NI; ++j) {
+            project_rows<FAST, T, NX>(full[j], A, ld, row0, n, bvec);
+            T o[RX];
+            extract_own<T, NX, RX, L>(full[j], l, o);
+#pragma unroll
+            for (int a = 0; a < RX; ++a) own[j][a] = xvl ? o[a] : own[j][a];
+        }
     };
-    auto planes_u = [&](T (&own)[RU], const T *A, int ld, int row0, int n, const T *bvec) {
-        T full[NU];
+    auto planes_u = [&](T (&own)[NI][RU], const T *A, int ld, int row0, int n, const T *bvec) {
+        T full[NI][NU];
         gather_u(own, full);
-        project_rows<FAST, T, NU>(full, A, ld, row0, n, bvec);
-        T o[RU];
-        extract_own<T, NU, RU, L>(full, l, o);
 #pragma unroll
-        for (int b = 0; b < RU; ++b) own[b] = uvl ? o[b] : own[b];
+        for (int j = 0; j < NI; ++j) {
+            project_rows<FAST, T, NU>(full[j], A, ld, row0, n, bvec);
+            T o[RU];
+            extract_own<T, NU, RU, L>(full[j], l, o);
+#pragma unroll
+            for (int b = 0; b < RU; ++b) own[j][b] = uvl ? o[b] : own[j][b];
+        }
     };
 
-    // ---- ring producers: all copies of one sweep step form one cp.async group ----
-    auto issue_fwd = [&](int k, int st) {
+    // ---- ring producers: all copies of one sweep step form one cp.async group.  cx / cu = this lane's rows in the record
+    // of knot point k (first instance of the group), xr / ur = its reference columns; sb = byte offset of the stage ----
+    auto issue_fwd = [&](int k, unsigned sb, const T *cx, const T *cu, const T *(&xr)[NI], const T *(&ur)[NI]) {
         if (k < N) {
-            const unsigned bx = aXl + (unsigned)st * STAGE, bu = aUl + (unsigned)st * STAGE;
-            const T *rx = gx + (int64_t)k * rec;
-            const T *ru = gu + (int64_t)k * rec;
-            if (xvl) {
-                cp_piece<RX * ES, CX>(bx, rx + LY.vnew);
-                cp_piece<RX * ES, CX>(bx + PXB, rx + LY.g);
-                cp_piece<RX * ES, ES>(bx + 2 * PXB, xrefp + (int64_t)k * NX);
-                if constexpr (EXT) {
+            const unsigned bx = aXl + sb, bu = aUl + sb;
 #pragma unroll
-                    for (int f = 0; f < 3; ++f)
-                        if (fx[f]) cp_piece<RX * ES, CX>(bx + (3 + f) * PXB, rx + LY.gf[f]);
+            for (int j = 0; j < NI; ++j) {
+                if (xvl) {
+                    cp_piece<RX * ES, CX>(bx + (0 * NI + j) * PXB, cx + REC::vnew + j * JX);
+                    cp_piece<RX * ES, CX>(bx + (1 * NI + j) * PXB, cx + REC::g + j * JX);
+                    cp_piece<RX * ES, ES>(bx + (2 * NI + j) * PXB, xr[j]);
+                    if constexpr ((FAM & 1) != 0)
+                        if (fx[0]) cp_piece<RX * ES, CX>(bx + ((3 + Cfg::fslot(0)) * NI + j) * PXB, cx + REC::gf(0) + j * JX);
+                    if constexpr ((FAM & 2) != 0)
+                        if (fx[1]) cp_piece<RX * ES, CX>(bx + ((3 + Cfg::fslot(1)) * NI + j) * PXB, cx + REC::gf(1) + j * JX);
+                    if constexpr ((FAM & 4) != 0)
+                        if (fx[2]) cp_piece<RX * ES, CX>(bx + ((3 + Cfg::fslot(2)) * NI + j) * PXB, cx + REC::gf(2) + j * JX);
                 }
-            }
-            if (uvl && k < N - 1) {
-                cp_piece<RU * ES, CU>(bu, ru + LY.d);
-                cp_piece<RU * ES, CU>(bu + PUB, ru + LY.znew);
-                cp_piece<RU * ES, CU>(bu + 2 * PUB, ru + LY.y);
-                if (has_uref) cp_piece<RU * ES, ES>(bu + 3 * PUB, urefp + (int64_t)k * NU);
-                if constexpr (EXT) {
-#pragma unroll
-                    for (int f = 0; f < 3; ++f)
-                        if (fu[f]) cp_piece<RU * ES, CU>(bu + (4 + f) * PUB, ru + LY.yf[f]);
+                if (uvl && k < N - 1) {
+                    cp_piece<RU * ES, CU>(bu + (0 * NI + j) * PUB, cu + REC::d + j * JU);
+                    cp_piece<RU * ES, CU>(bu + (1 * NI + j) * PUB, cu + REC::znew + j * JU);
+                    cp_piece<RU * ES, CU>(bu + (2 * NI + j) * PUB, cu + REC::y + j * JU);
+                    if (has_uref) cp_piece<RU * ES, ES>(bu + (3 * NI + j) * PUB, ur[j]);
+                    if constexpr ((FAM & 1) != 0)
+                        if (fu[0]) cp_piece<RU * ES, CU>(bu + ((4 + Cfg::fslot(0)) * NI + j) * PUB, cu + REC::yf(0) + j * JU);
+                    if constexpr ((FAM & 2) != 0)
+                        if (fu[1]) cp_piece<RU * ES, CU>(bu + ((4 + Cfg::fslot(1)) * NI + j) * PUB, cu + REC::yf(1) + j * JU);
+                    if constexpr ((FAM & 4) != 0)
+                        if (fu[2]) cp_piece<RU * ES, CU>(bu + ((4 + Cfg::fslot(2)) * NI + j) * PUB, cu + REC::yf(2) + j * JU);
                 }
             }
         }
         cp_commit();
     };
-    auto issue_bwd = [&](int k, int st) {
+    auto issue_bwd = [&](int k, unsigned sb, const T *cx, const T *cu) {
         if (k >= 0) {
-            const unsigned bx = aXl + (unsigned)st * STAGE, bu = aUl + (unsigned)st * STAGE;
-            if (xvl) cp_piece<RX * ES, CX>(bx, gx + (int64_t)k * rec + LY.q);
-            if (uvl && k < N - 1) cp_piece<RU * ES, CU>(bu, gu + (int64_t)k * rec + LY.r);
+            const unsigned bx = aXl + sb, bu = aUl + sb;
+#pragma unroll
+            for (int j = 0; j < NI; ++j) {
+                if (xvl) cp_piece<RX * ES, CX>(bx + j * PXB, cx + REC::q + j * JX);
+                if (uvl && k < N - 1) cp_piece<RU * ES, CU>(bu + j * PUB, cu + REC::r + j * JU);
+            }
         }
         cp_commit();
+    };
+
+    // hyperplane family F (1 static, 2 time-varying) of column k, state side then input side: slack = project(x + dual),
+    // dual += x - slack, cost -= rho (slack - dual)                  (admm.cpp:138-211, 240-255, 271-276, 284-289)
+    auto planes_family = [&](auto ftag, int k, const bool HASU, unsigned bx, unsigned bu, T *cx, T *cu, const T (&xo)[NI][RX],
+                             const T (&u)[NI][RU], T (&q)[NI][RX], T (&r)[NI][RU]) {
+        constexpr int F = decltype(ftag)::value;
+        constexpr int SL = Cfg::fslot(F);
+        if (fx[F]) {
+            T gf[NI][RX], sf[NI][RX];
+#pragma unroll
+            for (int j = 0; j < NI; ++j) {
+                lds_piece<T, RX, SX>(bx + ((3 + SL) * NI + j) * PXB, gf[j]);
+#pragma unroll
+                for (int a = 0; a < RX; ++a) sf[j][a] = xo[j][a] + gf[j][a];
+            }
+            if (F == 1) planes_x(sf, P.Alin_x, P.nlx, 0, P.nlx, P.blin_x);
+            else planes_x(sf, P.tv_Alin_x, P.ntvx * N, P.ntvx * k, P.ntvx, P.tv_blin_x + (int64_t)k * P.ntvx);
+#pragma unroll
+            for (int j = 0; j < NI; ++j) {
+                T gfn[RX];
+#pragma unroll
+                for (int a = 0; a < RX; ++a) {
+                    gfn[a] = (gf[j][a] + xo[j][a]) - sf[j][a];
+                    q[j][a] = nmac<FAST>(q[j][a], rho, sf[j][a] - gfn[a]);
+                }
+                if (xvl) {
+                    stg_piece<T, RX, CX>(cx + REC::gf(F) + j * JX, gfn);
+                    if (keep_f[F]) stg_piece<T, RX, CX>(wsb + (int64_t)k * recB + REC::vf(F) + (j * IPW + grp) * NX + l * RX, sf[j]);
+                }
+            }
+        }
+        if (fu[F] && HASU) {
+            T yf[NI][RU], sf[NI][RU];
+#pragma unroll
+            for (int j = 0; j < NI; ++j) {
+                lds_piece<T, RU, SU>(bu + ((4 + SL) * NI + j) * PUB, yf[j]);
+#pragma unroll
+                for (int b = 0; b < RU; ++b) sf[j][b] = u[j][b] + yf[j][b];
+            }
+            if (F == 1) planes_u(sf, P.Alin_u, P.nlu, 0, P.nlu, P.blin_u);
+            else planes_u(sf, P.tv_Alin_u, P.ntvu * (N - 1), P.ntvu * k, P.ntvu, P.tv_blin_u + (int64_t)k * P.ntvu);
+#pragma unroll
+            for (int j = 0; j < NI; ++j) {
+                T yfn[RU];
+#pragma unroll
+                for (int b = 0; b < RU; ++b) {
+                    yfn[b] = (yf[j][b] + u[j][b]) - sf[j][b];
+                    r[j][b] = nmac<FAST>(r[j][b], rho, sf[j][b] - yfn[b]);
+                }
+                if (uvl) {
+                    stg_piece<T, RU, CU>(cu + REC::yf(F) + j * JU, yfn);
+                    if (keep_f[F]) stg_piece<T, RU, CU>(wsb + (int64_t)k * recB + REC::zf(F) + (j * IPW + grp) * NU + l * RU, sf[j]);
+                }
+            }
+        }
     };
 
     // ---- forward sweep: rollout (admm.cpp:25-32) fused with update_slack (:81-213), update_dual (:219-256), the
     // residual maxima of termination_condition (:310-328) and the NEXT iteration's update_linear_cost (:262-304) ----
-    auto forward = [&](T &rpx, T &rdx, T &rpu, T &rdu) {
-        T xo[RX], Xf[NX];
+    auto forward = [&](T (&rpx)[NI], T (&rdx)[NI], T (&rpu)[NI], T (&rdu)[NI]) {
+        T xo[NI][RX], Xf[NI][NX];
+        const T *xr[NI], *ur[NI];  // reference columns of the knot point D steps ahead (what the next issue fetches)
 #pragma unroll
-        for (int a = 0; a < RX; ++a) xo[a] = x0o[a];
-        for (int j = 0; j < D; ++j) issue_fwd(j, j);
+        for (int j = 0; j < NI; ++j) {
+#pragma unroll
+            for (int a = 0; a < RX; ++a) xo[j][a] = x0o[j][a];
+            xr[j] = xrefp[j];
+            ur[j] = urefp[j];
+        }
+        T *cx = px0, *cu = pu0;  // this lane's rows in the record of the CURRENT knot point
+#pragma unroll
+        for (int t = 0; t < D; ++t) {
+            issue_fwd(t, (unsigned)t * STAGE, cx + t * recA, cu + t * recA, xr, ur);
+#pragma unroll
+            for (int j = 0; j < NI; ++j) {
+                xr[j] += NX;
+                ur[j] += NU;
+            }
+        }
         gather_x(xo, Xf);
-        int st = 0, sti = D % S;
+        unsigned sb = 0, sbi = (unsigned)(D % S) * STAGE;  // stage (byte offset) of the current step / of the step being fetched
         auto column = [&](int k, const bool HASU) {  // always inlined with a literal HASU
-            issue_fwd(k + D, sti);
+            issue_fwd(k + D, sbi, cx + D * recA, cu + D * recA, xr, ur);
             cp_wait(D);
-            const unsigned bx = aXl + (unsigned)st * STAGE, bu = aUl + (unsigned)st * STAGE;
-            T vo[RX], g[RX], xr[RX];
-            lds_piece<T, RX, SX>(bx, vo);
-            lds_piece<T, RX, SX>(bx + PXB, g);
-            lds_piece<T, RX, SX>(bx + 2 * PXB, xr);
-            T t1[RX + RU], u[RU], Uf[NU];
+            const unsigned bx = aXl + sb, bu = aUl + sb;
+            T t1[NI][RX + RU], u[NI][RU], Uf[NI][NU];
 #pragma unroll
-            for (int b = 0; b < RU; ++b) u[b] = T(0);
+            for (int j = 0; j < NI; ++j)
+#pragma unroll
+                for (int b = 0; b < RU; ++b) u[j][b] = T(0);
             if (HASU) {
-                T dk[RU];
-                lds_piece<T, RU, SU>(bu, dk);
-                dots<FAST>(mS1f, Xf, t1);  // [A x_k ; Kinf x_k]
+                T dk[NI][RU];
 #pragma unroll
-                for (int b = 0; b < RU; ++b) u[b] = (-t1[RX + b]) - dk[b];  // u_k = -(Kinf x_k) - d_k
+                for (int j = 0; j < NI; ++j) lds_piece<T, RU, SU>(bu + (0 * NI + j) * PUB, dk[j]);
+#pragma unroll
+                for (int j = 0; j < NI; ++j) dots<FAST>(mS1f, Xf[j], t1[j]);  // [A x_k ; Kinf x_k]
+#pragma unroll
+                for (int j = 0; j < NI; ++j)
+#pragma unroll
+                    for (int b = 0; b < RU; ++b) u[j][b] = (-t1[j][RX + b]) - dk[j][b];  // u_k = -(Kinf x_k) - d_k
                 gather_u(u, Uf);
             }
             if (tvb) {
@@ -448,104 +625,125 @@ __global__ void __launch_bounds__(GPS_MAX_WARPS * 32, 1)
                     }
                 }
             }
-            T *const wx = gx + (int64_t)k * rec;
-            T *const wu = gu + (int64_t)k * rec;
-            {   // state column k
-                T vn[RX], gn[RX], q[RX];
+            // ---- box constraints: state column k and input column k ----
+            T q[NI][RX], r[NI][RU];
+#pragma unroll
+            for (int j = 0; j < NI; ++j) {
+                T vo[RX], g[RX], xrf[RX], vn[RX], gn[RX];
+                lds_piece<T, RX, SX>(bx + (0 * NI + j) * PXB, vo);
+                lds_piece<T, RX, SX>(bx + (1 * NI + j) * PXB, g);
+                lds_piece<T, RX, SX>(bx + (2 * NI + j) * PXB, xrf);
 #pragma unroll
                 for (int a = 0; a < RX; ++a) {
-                    const T v = clamp_box<FAST>(xo[a] + g[a], loX[a], hiX[a]);  // vnew = clamp(x + g)
+                    const T v = clamp_box<FAST>(xo[j][a] + g[a], loX[a], hiX[a]);  // vnew = clamp(x + g)
                     vn[a] = v;
-                    gn[a] = (g[a] + xo[a]) - v;                                   // g += x - vnew
-                    rpx = absmax(rpx, xo[a] - v);
-                    rdx = absmax(rdx, vo[a] - v);
+                    gn[a] = (g[a] + xo[j][a]) - v;                                  // g += x - vnew
+                    rpx[j] = absmax(rpx[j], xo[j][a] - v);
+                    rdx[j] = absmax(rdx[j], vo[a] - v);
                     // k < N-1: q_k = -(xref*Q) - rho (vnew - g);  k = N-1: p_{N-1} = -(Pinf^T xref) - rho (vnew - g)
-                    const T base = HASU ? -(xr[a] * vQd[a]) : pterm[a];
-                    q[a] = nmac<FAST>(base, rho, v - gn[a]);
+                    const T base = HASU ? -(xrf[a] * vQd[a]) : pterm[j][a];
+                    q[j][a] = nmac<FAST>(base, rho, v - gn[a]);
                 }
                 if (xvl) {
-                    stg_piece<T, RX, CX>(wx + LY.vnew, vn);
-                    stg_piece<T, RX, CX>(wx + LY.g, gn);
-                    if (keep_v) stg_piece<T, RX, CX>(wx + LY.vprev, vo);
+                    stg_piece<T, RX, CX>(cx + REC::vnew + j * JX, vn);
+                    stg_piece<T, RX, CX>(cx + REC::g + j * JX, gn);
+                    if (keep_v) stg_piece<T, RX, CX>(wsb + (int64_t)k * recB + REC::vprev + (j * IPW + grp) * NX + l * RX, vo);
                 }
-                if constexpr (EXT) {
 #pragma unroll
-                    for (int f = 0; f < 3; ++f) {
-                        if (fx[f]) {  // warp-uniform
-                            T gf[RX], sf[RX], gfn[RX];
-                            lds_piece<T, RX, SX>(bx + (3 + f) * PXB, gf);
+                for (int b = 0; b < RU; ++b) r[j][b] = T(0);
+                if (HASU) {
+                    T zo[RU], y[RU], urf[RU], zn[RU], yn[RU];
+                    lds_piece<T, RU, SU>(bu + (1 * NI + j) * PUB, zo);
+                    lds_piece<T, RU, SU>(bu + (2 * NI + j) * PUB, y);
+                    lds_piece<T, RU, SU>(bu + (3 * NI + j) * PUB, urf);
 #pragma unroll
-                            for (int a = 0; a < RX; ++a) sf[a] = xo[a] + gf[a];
-                            if (f == 0) cones_x(sf);
-                            else if (f == 1) planes_x(sf, P.Alin_x, P.nlx, 0, P.nlx, P.blin_x);
-                            else planes_x(sf, P.tv_Alin_x, P.ntvx * N, P.ntvx * k, P.ntvx, P.tv_blin_x + (int64_t)k * P.ntvx);
+                    for (int b = 0; b < RU; ++b) {
+                        const T z = clamp_box<FAST>(u[j][b] + y[b], loU[b], hiU[b]);
+                        zn[b] = z;
+                        yn[b] = (y[b] + u[j][b]) - z;
+                        rpu[j] = absmax(rpu[j], u[j][b] - z);
+                        rdu[j] = absmax(rdu[j], zo[b] - z);
+                        const T urb = has_uref ? urf[b] : T(0);
+                        r[j][b] = nmac<FAST>(-(urb * vRd[b]), rho, z - yn[b]);
+                    }
+                    if (uvl) {
+                        stg_piece<T, RU, CU>(cu + REC::znew + j * JU, zn);
+                        stg_piece<T, RU, CU>(cu + REC::y + j * JU, yn);
+                        if (keep_v) stg_piece<T, RU, CU>(wsb + (int64_t)k * recB + REC::zprev + (j * IPW + grp) * NU + l * RU, zo);
+                    }
+                }
+            }
+            // ---- cones (family 0): state and input side together ----
+            if constexpr ((FAM & 1) != 0) {
+                if (fx[0] || (fu[0] && HASU)) {  // warp-uniform
+                    constexpr int SL = Cfg::fslot(0);
+                    T gf[NI][RX], sx[NI][RX], yf[NI][RU], su[NI][RU];
+#pragma unroll
+                    for (int j = 0; j < NI; ++j) {
+                        lds_piece<T, RX, SX>(bx + ((3 + SL) * NI + j) * PXB, gf[j]);
+                        lds_piece<T, RU, SU>(bu + ((4 + SL) * NI + j) * PUB, yf[j]);
+#pragma unroll
+                        for (int a = 0; a < RX; ++a) sx[j][a] = xo[j][a] + gf[j][a];
+#pragma unroll
+                        for (int b = 0; b < RU; ++b) su[j][b] = u[j][b] + yf[j][b];
+                    }
+                    cones_xu(sx, su, HASU);
+#pragma unroll
+                    for (int j = 0; j < NI; ++j) {
+                        if (fx[0]) {
+                            T gfn[RX];
 #pragma unroll
                             for (int a = 0; a < RX; ++a) {
-                                gfn[a] = (gf[a] + xo[a]) - sf[a];
-                                q[a] = nmac<FAST>(q[a], rho, sf[a] - gfn[a]);
+                                gfn[a] = (gf[j][a] + xo[j][a]) - sx[j][a];
+                                q[j][a] = nmac<FAST>(q[j][a], rho, sx[j][a] - gfn[a]);
                             }
                             if (xvl) {
-                                stg_piece<T, RX, CX>(wx + LY.gf[f], gfn);
-                                if (LY.vf[f] >= 0) stg_piece<T, RX, CX>(wx + LY.vf[f], sf);
+                                stg_piece<T, RX, CX>(cx + REC::gf(0) + j * JX, gfn);
+                                if (keep_f[0]) stg_piece<T, RX, CX>(wsb + (int64_t)k * recB + REC::vf(0) + (j * IPW + grp) * NX + l * RX, sx[j]);
                             }
                         }
-                    }
-                }
-                if (xvl) stg_piece<T, RX, CX>(wx + LY.q, q);
-            }
-            if (HASU) {  // input column k and the rollout step
-                T zo[RU], y[RU], ur[RU], zn[RU], yn[RU], r[RU];
-                lds_piece<T, RU, SU>(bu + PUB, zo);
-                lds_piece<T, RU, SU>(bu + 2 * PUB, y);
-                lds_piece<T, RU, SU>(bu + 3 * PUB, ur);
-#pragma unroll
-                for (int b = 0; b < RU; ++b) {
-                    const T z = clamp_box<FAST>(u[b] + y[b], loU[b], hiU[b]);
-                    zn[b] = z;
-                    yn[b] = (y[b] + u[b]) - z;
-                    rpu = absmax(rpu, u[b] - z);
-                    rdu = absmax(rdu, zo[b] - z);
-                    const T urb = has_uref ? ur[b] : T(0);
-                    r[b] = nmac<FAST>(-(urb * vRd[b]), rho, z - yn[b]);
-                }
-                if (uvl) {
-                    stg_piece<T, RU, CU>(wu + LY.znew, zn);
-                    stg_piece<T, RU, CU>(wu + LY.y, yn);
-                    if (keep_v) stg_piece<T, RU, CU>(wu + LY.zprev, zo);
-                }
-                if constexpr (EXT) {
-#pragma unroll
-                    for (int f = 0; f < 3; ++f) {
-                        if (fu[f]) {
-                            T yf[RU], sf[RU], yfn[RU];
-                            lds_piece<T, RU, SU>(bu + (4 + f) * PUB, yf);
-#pragma unroll
-                            for (int b = 0; b < RU; ++b) sf[b] = u[b] + yf[b];
-                            if (f == 0) cones_u(sf);
-                            else if (f == 1) planes_u(sf, P.Alin_u, P.nlu, 0, P.nlu, P.blin_u);
-                            else planes_u(sf, P.tv_Alin_u, P.ntvu * (N - 1), P.ntvu * k, P.ntvu, P.tv_blin_u + (int64_t)k * P.ntvu);
+                        if (fu[0] && HASU) {
+                            T yfn[RU];
 #pragma unroll
                             for (int b = 0; b < RU; ++b) {
-                                yfn[b] = (yf[b] + u[b]) - sf[b];
-                                r[b] = nmac<FAST>(r[b], rho, sf[b] - yfn[b]);
+                                yfn[b] = (yf[j][b] + u[j][b]) - su[j][b];
+                                r[j][b] = nmac<FAST>(r[j][b], rho, su[j][b] - yfn[b]);
                             }
                             if (uvl) {
-                                stg_piece<T, RU, CU>(wu + LY.yf[f], yfn);
-                                if (LY.zf[f] >= 0) stg_piece<T, RU, CU>(wu + LY.zf[f], sf);
+                                stg_piece<T, RU, CU>(cu + REC::yf(0) + j * JU, yfn);
+                                if (keep_f[0]) stg_piece<T, RU, CU>(wsb + (int64_t)k * recB + REC::zf(0) + (j * IPW + grp) * NU + l * RU, su[j]);
                             }
                         }
                     }
                 }
-                if (uvl) stg_piece<T, RU, CU>(wu + LY.r, r);
-                // x_{k+1} = (A x_k + B u_k) + f                                            (admm.cpp:30)
-                T bu_[RX];
-                dots<FAST>(mB, Uf, bu_);
+            }
+            // ---- hyperplanes (families 1, 2) ----
+            if constexpr ((FAM & 2) != 0) planes_family(IdxTag<1>{}, k, HASU, bx, bu, cx, cu, xo, u, q, r);
+            if constexpr ((FAM & 4) != 0) planes_family(IdxTag<2>{}, k, HASU, bx, bu, cx, cu, xo, u, q, r);
 #pragma unroll
-                for (int a = 0; a < RX; ++a) xo[a] = (t1[a] + bu_[a]) + vf[a];
+            for (int j = 0; j < NI; ++j) {
+                if (xvl) stg_piece<T, RX, CX>(cx + REC::q + j * JX, q[j]);
+                if (HASU && uvl) stg_piece<T, RU, CU>(cu + REC::r + j * JU, r[j]);
+            }
+            if (HASU) {  // x_{k+1} = (A x_k + B u_k) + f                                  (admm.cpp:30)
+#pragma unroll
+                for (int j = 0; j < NI; ++j) {
+                    T bu_[RX];
+                    dots<FAST>(mB, Uf[j], bu_);
+#pragma unroll
+                    for (int a = 0; a < RX; ++a) xo[j][a] = (t1[j][a] + bu_[a]) + vf[a];
+                }
                 gather_x(xo, Xf);
             }
-            st = (st + 1 == S) ? 0 : st + 1;
-            sti = (sti + 1 == S) ? 0 : sti + 1;
+            cx += recA;
+            cu += recA;
+#pragma unroll
+            for (int j = 0; j < NI; ++j) {
+                xr[j] += NX;
+                ur[j] += NU;
+            }
+            sb = (sb + STAGE == S * STAGE) ? 0u : sb + STAGE;
+            sbi = (sbi + STAGE == S * STAGE) ? 0u : sbi + STAGE;
         };
         for (int k = 0; k < N - 1; ++k) column(k, true);
         column(N - 1, false);
@@ -553,46 +751,69 @@ __global__ void __launch_bounds__(GPS_MAX_WARPS * 32, 1)
 
     // ---- backward sweep (admm.cpp:13-20) on the stored linear cost ----
     auto backward = [&]() {
-        for (int j = 0; j < D; ++j) issue_bwd(N - 1 - j, j);
-        int st = 0, sti = D % S;
-        T po[RX], Pf[NX];
+        T *cx = px0 + (int64_t)(N - 1) * recA, *cu = pu0 + (int64_t)(N - 1) * recA;  // record of the current knot point
+#pragma unroll
+        for (int t = 0; t < D; ++t) issue_bwd(N - 1 - t, (unsigned)t * STAGE, cx - t * recA, cu - t * recA);
+        unsigned sb = 0, sbi = (unsigned)(D % S) * STAGE;
+        T po[NI][RX], Pf[NI][NX];
         {   // terminal cost p_{N-1}
-            issue_bwd(N - 1 - D, sti);
+            issue_bwd(N - 1 - D, sbi, cx - D * recA, cu - D * recA);
             cp_wait(D);
-            lds_piece<T, RX, SX>(aXl + (unsigned)st * STAGE, po);
+#pragma unroll
+            for (int j = 0; j < NI; ++j) lds_piece<T, RX, SX>(aXl + sb + j * PXB, po[j]);
             gather_x(po, Pf);
-            st = (st + 1 == S) ? 0 : st + 1;
-            sti = (sti + 1 == S) ? 0 : sti + 1;
+            cx -= recA;
+            cu -= recA;
+            sb = (sb + STAGE == S * STAGE) ? 0u : sb + STAGE;
+            sbi = (sbi + STAGE == S * STAGE) ? 0u : sbi + STAGE;
         }
         for (int k = N - 2; k >= 0; --k) {
-            issue_bwd(k - D, sti);
+            issue_bwd(k - D, sbi, cx - D * recA, cu - D * recA);
             cp_wait(D);
-            T q[RX], r[RU], Rf[NU];
-            lds_piece<T, RX, SX>(aXl + (unsigned)st * STAGE, q);
-            lds_piece<T, RU, SU>(aUl + (unsigned)st * STAGE, r);
+            T q[NI][RX], r[NI][RU], Rf[NI][NU];
+#pragma unroll
+            for (int j = 0; j < NI; ++j) {
+                lds_piece<T, RX, SX>(aXl + sb + j * PXB, q[j]);
+                lds_piece<T, RU, SU>(aUl + sb + j * PUB, r[j]);
+            }
             gather_u(r, Rf);
             // d_k = Quu_inv ((B^T p_{k+1} + r_k) + BPf)
-            T s_[RU], Sf[NU], acc1[RX + RU], kr[RX], dq[RU];
-            dots<FAST>(mS1b, Pf, acc1);  // [AmBKt p_{k+1} ; B^T p_{k+1}]
+            T s_[NI][RU], Sf[NI][NU], acc1[NI][RX + RU];
 #pragma unroll
-            for (int b = 0; b < RU; ++b) s_[b] = (acc1[RX + b] + r[b]) + vBPf[b];
+            for (int j = 0; j < NI; ++j) {
+                dots<FAST>(mS1b, Pf[j], acc1[j]);  // [AmBKt p_{k+1} ; B^T p_{k+1}]
+#pragma unroll
+                for (int b = 0; b < RU; ++b) s_[j][b] = (acc1[j][RX + b] + r[j][b]) + vBPf[b];
+            }
             gather_u(s_, Sf);
             // p_k = ((q_k + AmBKt p_{k+1}) - Kinf^T r_k) + APf
-            dots<FAST>(mKt, Rf, kr);
 #pragma unroll
-            for (int a = 0; a < RX; ++a) po[a] = ((q[a] + acc1[a]) - kr[a]) + vAPf[a];
+            for (int j = 0; j < NI; ++j) {
+                T kr[RX];
+                dots<FAST>(mKt, Rf[j], kr);
+#pragma unroll
+                for (int a = 0; a < RX; ++a) po[j][a] = ((q[j][a] + acc1[j][a]) - kr[a]) + vAPf[a];
+            }
             if (k > 0) gather_x(po, Pf);  // p_0 itself is never used
-            dots<FAST>(mQuu, Sf, dq);
-            if (uvl) stg_piece<T, RU, CU>(gu + (int64_t)k * rec + LY.d, dq);
-            st = (st + 1 == S) ? 0 : st + 1;
-            sti = (sti + 1 == S) ? 0 : sti + 1;
+#pragma unroll
+            for (int j = 0; j < NI; ++j) {
+                T dq[RU];
+                dots<FAST>(mQuu, Sf[j], dq);
+                if (uvl) stg_piece<T, RU, CU>(cu + REC::d + j * JU, dq);
+            }
+            cx -= recA;
+            cu -= recA;
+            sb = (sb + STAGE == S * STAGE) ? 0u : sb + STAGE;
+            sbi = (sbi + STAGE == S * STAGE) ? 0u : sbi + STAGE;
         }
     };
 
-    // ---- cooperative (all 32 lanes) load of instance `ib` into slot `s`: the slot's records are initialised from the
-    // warm-start state (zeros when cold), including the first iteration's linear cost (admm.cpp:262-304 on the state
-    // as solve() finds it, cone / hyperplane slacks = previous rollout, admm.cpp:352-376) ----
-    auto load_slot = [&](int s, int64_t ib) {
+    // ---- cooperative (all 32 lanes) load of instance `ib` into slot (group s, instance J of the group): the slot's
+    // records are initialised from the warm-start state (zeros when cold), including the first iteration's linear cost
+    // (admm.cpp:262-304 on the state as solve() finds it; cone / hyperplane slacks = previous rollout, admm.cpp:352-376) ----
+    auto load_slot = [&](auto jtag, int s, int64_t ib) {
+        constexpr int J = decltype(jtag)::value;
+        const int sidx = J * IPW + s;
         const int64_t ox = ib * (int64_t)N * NX, ou = ib * (int64_t)(N - 1) * NU;
         const T *xrefb = P.Xref + (P.xref_pi ? ox : 0);
         const T *urefb = has_uref ? P.Uref + (P.uref_pi ? ou : 0) : nullptr;
@@ -613,22 +834,23 @@ __global__ void __launch_bounds__(GPS_MAX_WARPS * 32, 1)
                 acc = -sacc;
             }
             acc = nmac<FAST>(acc, rho, vnew_in - g_in);
-            T *r_ = wsw + (int64_t)k * rec + s * NX + i;
-            r_[LY.vnew] = v_in;  // the slot of the box slack holds work->v until the first forward sweep rewrites it
-            r_[LY.g] = g_in;
+            T *r_ = wsw + (int64_t)k * recA + sidx * NX + i;
+            T *rb_ = wsb + (int64_t)k * recB + sidx * NX + i;
+            r_[REC::vnew] = v_in;  // the slot of the box slack holds work->v until the first forward sweep rewrites it
+            r_[REC::g] = g_in;
             if constexpr (EXT) {
                 const T xin = (k == 0) ? __ldg(P.x0 + ib * NX + i) : ((!cold && P.s_x) ? P.s_x[ox + e] : T(0));
 #pragma unroll
                 for (int f = 0; f < 3; ++f) {
-                    if (fx[f]) {
+                    if (((FAM >> f) & 1) && fx[f]) {
                         const T gf_in = (!cold && sgf[f]) ? sgf[f][ox + e] : T(0);
                         acc = nmac<FAST>(acc, rho, xin - gf_in);
-                        r_[LY.gf[f]] = gf_in;
-                        if (LY.vf[f] >= 0) r_[LY.vf[f]] = xin;
+                        r_[REC::gf(f)] = gf_in;
+                        if (keep_f[f]) rb_[REC::vf(f)] = xin;
                     }
                 }
             }
-            r_[LY.q] = acc;
+            r_[REC::q] = acc;
         }
         for (int e = lane; e < (N - 1) * NU; e += 32) {
             const int k = e / NU, j = e - k * NU;
@@ -637,54 +859,57 @@ __global__ void __launch_bounds__(GPS_MAX_WARPS * 32, 1)
             const T z_in = (!cold && P.s_z) ? P.s_z[ou + e] : T(0);
             const T ur = has_uref ? __ldg(urefb + e) : T(0);
             T acc = nmac<FAST>(-(ur * __ldg(gmat + OFF_RD + j)), rho, znew_in - y_in);
-            T *r_ = wsw + (int64_t)k * rec + s * NU + j;
-            r_[LY.znew] = z_in;
-            r_[LY.y] = y_in;
+            T *r_ = wsw + (int64_t)k * recA + sidx * NU + j;
+            T *rb_ = wsb + (int64_t)k * recB + sidx * NU + j;
+            r_[REC::znew] = z_in;
+            r_[REC::y] = y_in;
             if constexpr (EXT) {
                 const T uin = (!cold && P.s_u) ? P.s_u[ou + e] : T(0);
 #pragma unroll
                 for (int f = 0; f < 3; ++f) {
-                    if (fu[f]) {
+                    if (((FAM >> f) & 1) && fu[f]) {
                         const T yf_in = (!cold && syf[f]) ? syf[f][ou + e] : T(0);
                         acc = nmac<FAST>(acc, rho, uin - yf_in);
-                        r_[LY.yf[f]] = yf_in;
-                        if (LY.zf[f] >= 0) r_[LY.zf[f]] = uin;
+                        r_[REC::yf(f)] = yf_in;
+                        if (keep_f[f]) rb_[REC::zf(f)] = uin;
                     }
                 }
             }
-            r_[LY.r] = acc;
+            r_[REC::r] = acc;
         }
-        if (slot == s) {
-            inst = ib;
-            busy = true;
-            it = 0;
-            solved = 0;
-            res_px = res_dx = res_pu = res_du = T(0);
-            xrefp = xrefb + l * RX;
-            urefp = has_uref ? urefb + l * RU : P.Xref;
+        if (grp == s) {
+            inst[J] = ib;
+            busy[J] = true;
+            it[J] = 0;
+            solved[J] = 0;
+            res_px[J] = res_dx[J] = res_pu[J] = res_du[J] = T(0);
+            xrefp[J] = xrefb + l * RX;
+            urefp[J] = has_uref ? urefb + l * RU : P.Xref;
             const T *xl = xrefb + (int64_t)(N - 1) * NX;
 #pragma unroll
             for (int a = 0; a < RX; ++a) {
                 const int ii = xvl ? l * RX + a : 0;
-                x0o[a] = xvl ? __ldg(P.x0 + ib * NX + ii) : T(0);
+                x0o[J][a] = xvl ? __ldg(P.x0 + ib * NX + ii) : T(0);
                 T sacc = __ldg(xl) * __ldg(gmat + OFF_PINF + NX * ii);
                 for (int m = 1; m < NX; ++m) sacc = mac<FAST>(sacc, __ldg(xl + m), __ldg(gmat + OFF_PINF + m + NX * ii));
-                pterm[a] = xvl ? -sacc : T(0);
+                pterm[J][a] = xvl ? -sacc : T(0);
             }
         }
         __syncwarp();  // the records were written by all lanes; their owners read them from here on
     };
 
-    // ---- cooperative write-back of slot `s` (instance `ib`) ----
-    auto store_slot = [&](int s, int64_t ib) {
-        const int s_solved = __shfl_sync(0xffffffffu, solved, s * L);
-        const int s_it = __shfl_sync(0xffffffffu, it, s * L);
-        if (slot == s && l == 0) {
-            if (P.iter) P.iter[ib] = it;
-            if (P.solved) P.solved[ib] = solved;
+    // ---- cooperative write-back of slot (group s, instance J of the group) holding instance `ib` ----
+    auto store_slot = [&](auto jtag, int s, int64_t ib) {
+        constexpr int J = decltype(jtag)::value;
+        const int sidx = J * IPW + s;
+        const int s_solved = __shfl_sync(0xffffffffu, solved[J], s * L);
+        const int s_it = __shfl_sync(0xffffffffu, it[J], s * L);
+        if (grp == s && l == 0) {
+            if (P.iter) P.iter[ib] = it[J];
+            if (P.solved) P.solved[ib] = solved[J];
             if (P.residuals) {
                 T *r = P.residuals + 4 * ib;
-                r[0] = res_px; r[1] = res_dx; r[2] = res_pu; r[3] = res_du;
+                r[0] = res_px[J]; r[1] = res_dx[J]; r[2] = res_pu[J]; r[3] = res_du[J];
             }
         }
         __syncwarp();  // owner lanes wrote the records; every lane reads them below
@@ -696,85 +921,97 @@ __global__ void __launch_bounds__(GPS_MAX_WARPS * 32, 1)
         T *const oyf[3] = {P.s_yc, P.s_yl, P.s_yl_tv};
         for (int e = lane; e < N * NX; e += 32) {
             const int k = e / NX, i = e - k * NX;
-            const T *r_ = wsw + (int64_t)k * rec + s * NX + i;
+            const T *r_ = wsw + (int64_t)k * recA + sidx * NX + i;
+            const T *rb_ = wsb + (int64_t)k * recB + sidx * NX + i;
             // solution->x = vnew (admm.cpp:436,452); no iteration (max_iter <= 0): the state as it came in
-            const T v = ran ? r_[LY.vnew] : ((!cold && P.s_vnew) ? P.s_vnew[ox + e] : T(0));
+            const T v = ran ? r_[REC::vnew] : ((!cold && P.s_vnew) ? P.s_vnew[ox + e] : T(0));
             if (P.sol_x) P.sol_x[ox + e] = v;
             if (P.s_vnew) P.s_vnew[ox + e] = v;
-            if (P.s_g) P.s_g[ox + e] = r_[LY.g];
+            if (P.s_g) P.s_g[ox + e] = r_[REC::g];
             // work->v: previous vnew when the solve converged (the return at admm.cpp:441 precedes :445), else = vnew
-            if (P.s_v && ran) P.s_v[ox + e] = s_solved ? r_[LY.vprev] : v;
+            if (P.s_v && ran) P.s_v[ox + e] = s_solved ? rb_[REC::vprev] : v;
             else if (P.s_v && cold) P.s_v[ox + e] = T(0);
             if constexpr (EXT) {
 #pragma unroll
                 for (int f = 0; f < 3; ++f) {
-                    if (fx[f]) {
-                        if (ovf[f]) ovf[f][ox + e] = r_[LY.vf[f]];
-                        if (ogf[f]) ogf[f][ox + e] = r_[LY.gf[f]];
+                    if (((FAM >> f) & 1) && fx[f]) {
+                        if (ovf[f]) ovf[f][ox + e] = rb_[REC::vf(f)];
+                        if (ogf[f]) ogf[f][ox + e] = r_[REC::gf(f)];
                     }
                 }
             }
         }
         for (int e = lane; e < (N - 1) * NU; e += 32) {
             const int k = e / NU, j = e - k * NU;
-            const T *r_ = wsw + (int64_t)k * rec + s * NU + j;
-            const T z = ran ? r_[LY.znew] : ((!cold && P.s_znew) ? P.s_znew[ou + e] : T(0));
+            const T *r_ = wsw + (int64_t)k * recA + sidx * NU + j;
+            const T *rb_ = wsb + (int64_t)k * recB + sidx * NU + j;
+            const T z = ran ? r_[REC::znew] : ((!cold && P.s_znew) ? P.s_znew[ou + e] : T(0));
             if (P.sol_u) P.sol_u[ou + e] = z;
             if (P.s_znew) P.s_znew[ou + e] = z;
-            if (P.s_y) P.s_y[ou + e] = r_[LY.y];
-            if (P.s_z && ran) P.s_z[ou + e] = s_solved ? r_[LY.zprev] : z;
+            if (P.s_y) P.s_y[ou + e] = r_[REC::y];
+            if (P.s_z && ran) P.s_z[ou + e] = s_solved ? rb_[REC::zprev] : z;
             else if (P.s_z && cold) P.s_z[ou + e] = T(0);
             if constexpr (EXT) {
 #pragma unroll
                 for (int f = 0; f < 3; ++f) {
-                    if (fu[f]) {
-                        if (ozf[f]) ozf[f][ou + e] = r_[LY.zf[f]];
-                        if (oyf[f]) oyf[f][ou + e] = r_[LY.yf[f]];
+                    if (((FAM >> f) & 1) && fu[f]) {
+                        if (ozf[f]) ozf[f][ou + e] = rb_[REC::zf(f)];
+                        if (oyf[f]) oyf[f][ou + e] = r_[REC::yf(f)];
                     }
                 }
             }
         }
         // work->x / work->u (and u0 = work->u.col(0)): replay of the last rollout from d and x0, bit-identical to the last
-        // forward sweep.  Every lane executes the arithmetic (the gathers are warp-wide); the lanes of slot s store.
+        // forward sweep.  Every lane executes the arithmetic (the gathers are warp-wide); the lanes of group s store.
         if (P.s_x || P.s_u || P.u0) {
             __syncwarp();
-            const bool mine = slot == s;
-            T xo[RX], Xf[NX];
+            const bool mine = grp == s;
+            T xo[NI][RX], Xf[NI][NX];
 #pragma unroll
-            for (int a = 0; a < RX; ++a) xo[a] = x0o[a];
+            for (int j = 0; j < NI; ++j)
+#pragma unroll
+                for (int a = 0; a < RX; ++a) xo[j][a] = x0o[j][a];
             gather_x(xo, Xf);
             const int kend = (P.s_x || P.s_u) ? N : 1;
             for (int k = 0; k < kend; ++k) {
                 if (P.s_x && mine && xvl) {
 #pragma unroll
                     for (int a = 0; a < RX; ++a) {
-                        if (ran || k == 0) P.s_x[ox + (int64_t)k * NX + l * RX + a] = xo[a];
+                        if (ran || k == 0) P.s_x[ox + (int64_t)k * NX + l * RX + a] = xo[J][a];
                         else if (cold) P.s_x[ox + (int64_t)k * NX + l * RX + a] = T(0);
                     }
                 }
                 if (k < N - 1) {
-                    T u[RU], Uf[NU], t1[RX + RU], bu_[RX], dk[RU];
+                    T u[NI][RU], Uf[NI][NU], t1[NI][RX + RU];
 #pragma unroll
-                    for (int b = 0; b < RU; ++b) dk[b] = (ran && uvl) ? gu[(int64_t)k * rec + LY.d + b] : T(0);
-                    dots<FAST>(mS1f, Xf, t1);
+                    for (int j = 0; j < NI; ++j) {
+                        T dk[RU];
 #pragma unroll
-                    for (int b = 0; b < RU; ++b) u[b] = (-t1[RX + b]) - dk[b];
+                        for (int b = 0; b < RU; ++b) dk[b] = (ran && uvl) ? pu0[(int64_t)k * recA + REC::d + j * JU + b] : T(0);
+                        dots<FAST>(mS1f, Xf[j], t1[j]);
+#pragma unroll
+                        for (int b = 0; b < RU; ++b) u[j][b] = (-t1[j][RX + b]) - dk[b];
+                    }
                     if (mine && uvl) {
 #pragma unroll
                         for (int b = 0; b < RU; ++b) {
                             const int64_t o = ou + (int64_t)k * NU + l * RU + b;
                             if (P.s_u) {
-                                if (ran) P.s_u[o] = u[b];
+                                if (ran) P.s_u[o] = u[J][b];
                                 else if (cold) P.s_u[o] = T(0);
                             }
-                            if (P.u0 && k == 0) P.u0[ib * NU + l * RU + b] = ran ? u[b] : ((!cold && P.s_u) ? P.s_u[o] : T(0));
+                            if (P.u0 && k == 0) P.u0[ib * NU + l * RU + b] = ran ? u[J][b] : ((!cold && P.s_u) ? P.s_u[o] : T(0));
                         }
                     }
                     if (k + 1 < kend) {
                         gather_u(u, Uf);
-                        dots<FAST>(mB, Uf, bu_);
 #pragma unroll
-                        for (int a = 0; a < RX; ++a) xo[a] = (t1[a] + bu_[a]) + vf[a];
+                        for (int j = 0; j < NI; ++j) {
+                            T bu_[RX];
+                            dots<FAST>(mB, Uf[j], bu_);
+#pragma unroll
+                            for (int a = 0; a < RX; ++a) xo[j][a] = (t1[j][a] + bu_[a]) + vf[a];
+                        }
                         gather_x(xo, Xf);
                     }
                 }
@@ -783,51 +1020,69 @@ __global__ void __launch_bounds__(GPS_MAX_WARPS * 32, 1)
         __syncwarp();
     };
 
+    // retire / refill the J-th instance of every group that needs it
+    auto service = [&](auto jtag) {
+        constexpr int J = decltype(jtag)::value;
+        const bool fin = busy[J] && (solved[J] || it[J] >= P.max_iter);
+        const unsigned todo = __ballot_sync(0xffffffffu, (fin || (!busy[J] && want[J])) && l == 0);
+        for (unsigned m = todo; m; m &= m - 1) {
+            const int s = (__ffs(m) - 1) / L;
+            const int64_t ib_old = __shfl_sync(0xffffffffu, inst[J], s * L);
+            const int was_busy = __shfl_sync(0xffffffffu, (int)busy[J], s * L);
+            unsigned long long nxt = 0;
+            if (lane == 0) nxt = atomicAdd(queue, 1ULL);
+            if (was_busy) store_slot(jtag, s, ib_old);
+            nxt = __shfl_sync(0xffffffffu, nxt, 0);
+            if ((int64_t)nxt < P.B) {
+                load_slot(jtag, s, (int64_t)nxt);
+            } else if (grp == s) {
+                busy[J] = false;
+                want[J] = false;
+            }
+        }
+    };
+
     // ---- persistent loop (same protocol as the on-chip kernel): retire / refill slots, then iterate until some
     // slot terminates; the iteration loop has warp-uniform control flow only ----
     for (;;) {
-        const bool fin = busy && (solved || it >= P.max_iter);
-        const unsigned todo = __ballot_sync(0xffffffffu, (fin || (!busy && want)) && l == 0);
-        for (unsigned m = todo; m; m &= m - 1) {
-            const int s = (__ffs(m) - 1) / L;
-            const int64_t ib_old = __shfl_sync(0xffffffffu, inst, s * L);
-            const int was_busy = __shfl_sync(0xffffffffu, (int)busy, s * L);
-            unsigned long long nxt = 0;
-            if (lane == 0) nxt = atomicAdd(queue, 1ULL);
-            if (was_busy) store_slot(s, ib_old);
-            nxt = __shfl_sync(0xffffffffu, nxt, 0);
-            if ((int64_t)nxt < P.B) {
-                load_slot(s, (int64_t)nxt);
-            } else if (slot == s) {
-                busy = false;
-                want = false;
-            }
+        service(IdxTag<0>{});
+        if constexpr (NI > 1) service(IdxTag<1>{});
+        bool anyb = false, over = false;
+#pragma unroll
+        for (int j = 0; j < NI; ++j) {
+            anyb = anyb || busy[j];
+            over = over || (busy[j] && it[j] >= P.max_iter);
         }
-        if (!__any_sync(0xffffffffu, busy)) break;
-        if (__any_sync(0xffffffffu, busy && it >= P.max_iter)) continue;  // max_iter <= 0: retire without iterating
+        if (!__any_sync(0xffffffffu, anyb)) break;
+        if (__any_sync(0xffffffffu, over)) continue;  // max_iter <= 0: retire without iterating
         __syncwarp();
+        bool stop;
         do {
             backward();
             __syncwarp();
-            T rpx = T(0), rdx = T(0), rpu = T(0), rdu = T(0);
+            T rpx[NI], rdx[NI], rpu[NI], rdu[NI];
+#pragma unroll
+            for (int j = 0; j < NI; ++j) rpx[j] = rdx[j] = rpu[j] = rdu[j] = T(0);
             forward(rpx, rdx, rpu, rdu);
             __syncwarp();
             // termination_condition (admm.cpp:310-328), per instance
-            rpx = group_max<T, L>(rpx);
-            rdx = group_max<T, L>(rdx);
-            rpu = group_max<T, L>(rpu);
-            rdu = group_max<T, L>(rdu);
-            if (busy) {
-                it += 1;
-                if (it % P.check_termination == 0) {
-                    res_px = rpx;
-                    res_dx = rdx * rho;
-                    res_pu = rpu;
-                    res_du = rdu * rho;
-                    if (res_px < P.pri_tol && res_pu < P.pri_tol && res_dx < P.dua_tol && res_du < P.dua_tol) solved = 1;
+            stop = false;
+#pragma unroll
+            for (int j = 0; j < NI; ++j) {
+                const T a = group_max<T, L>(rpx[j]), b = group_max<T, L>(rdx[j]), c = group_max<T, L>(rpu[j]), d = group_max<T, L>(rdu[j]);
+                if (busy[j]) {
+                    it[j] += 1;
+                    if (it[j] % P.check_termination == 0) {
+                        res_px[j] = a;
+                        res_dx[j] = b * rho;
+                        res_pu[j] = c;
+                        res_du[j] = d * rho;
+                        if (res_px[j] < P.pri_tol && res_pu[j] < P.pri_tol && res_dx[j] < P.dua_tol && res_du[j] < P.dua_tol) solved[j] = 1;
+                    }
                 }
+                stop = stop || (busy[j] && (solved[j] || it[j] >= P.max_iter));
             }
-        } while (!__any_sync(0xffffffffu, busy && (solved || it >= P.max_iter)));
+        } while (!__any_sync(0xffffffffu, stop));
     }
 }
 
@@ -835,7 +1090,7 @@ __global__ void __launch_bounds__(GPS_MAX_WARPS * 32, 1)
 // host side: record layout, resident-slot plan, launch
 // ---------------------------------------------------------------------------------------------------------
 struct GpsPlan {
-    int L = 0, warps = 0, ctas = 0, dist = 0;
+    int L = 0, NI = 0, warps = 0, ctas = 0;
     size_t smem = 0, ws_bytes = 0;
     GpsLayout ly;
 };
@@ -845,84 +1100,86 @@ inline int gps_env_int(const char *name, int dflt) {
     return e ? std::atoi(e) : dflt;
 }
 
-template <typename T, int NX, int NU, int L, bool EXT>
+template <typename T, int NX, int NU, int L, int NI, int FAM>
 inline GpsPlan gps_plan_L(const LaunchDesc &d) {
-    using Cfg = GpsCfg<NX, NU, L, (int)sizeof(T), EXT>;
+    using Cfg = GpsCfg<NX, NU, L, (int)sizeof(T), NI, FAM>;
+    using REC = GpsRec<NX, NU, Cfg::SPW, (int)sizeof(T), FAM>;
     GpsPlan p;
-    GpsLayout &ly = p.ly;
-    const int ES = (int)sizeof(T), IPW = Cfg::IPW;
-    int off = 0;
-    auto take = [&](bool present, int rows) {
-        if (!present) return -1;
-        const int o = off;
-        off += (IPW * rows * ES + 15) / 16 * 16 / ES;
-        return o;
-    };
+    const int SPW = Cfg::SPW;
     const tinympc_state_t &s = d.io.state;
-    const bool fx[3] = {EXT && d.soc_x, EXT && d.lin_x, EXT && d.tvl_x}, fu[3] = {EXT && d.soc_u, EXT && d.lin_u, EXT && d.tvl_u};
-    const void *ovf[3] = {s.vcnew, s.vlnew, s.vlnew_tv}, *ozf[3] = {s.zcnew, s.zlnew, s.zlnew_tv};
-    ly.d = take(true, NU);
-    ly.vnew = take(true, NX);
-    ly.g = take(true, NX);
-    for (int f = 0; f < 3; ++f) ly.gf[f] = take(fx[f], NX);
-    ly.znew = take(true, NU);
-    ly.y = take(true, NU);
-    for (int f = 0; f < 3; ++f) ly.yf[f] = take(fu[f], NU);
-    ly.q = take(true, NX);
-    ly.r = take(true, NU);
-    const bool keep_v = s.v || s.z;
-    ly.vprev = take(keep_v, NX);
-    ly.zprev = take(keep_v, NU);
-    for (int f = 0; f < 3; ++f) ly.vf[f] = take(fx[f] && ovf[f], NX);
-    for (int f = 0; f < 3; ++f) ly.zf[f] = take(fu[f] && ozf[f], NU);
-    ly.rec = off;
-    int dist = gps_env_int("TINYMPC_GPS_DIST", 2);
-    dist = std::max(1, std::min(3, dist));
+    // region B: previous box slacks (work->v / work->z) and family slacks, only when the caller wants them back
+    p.ly.has_b = (s.v || s.z || s.vcnew || s.zcnew || s.vlnew || s.zlnew || s.vlnew_tv || s.zlnew_tv) ? 1 : 0;
     const int max_smem = d.max_smem_optin - 64;
     const size_t blob = ((size_t)(3 * NX * NX + 2 * NX * NU + NU * NU + 4 * NX + 2 * NU) * sizeof(T) + 15) / 16 * 16 + 64;
-    while (dist > 1 && Cfg::warp_bytes(dist + 1) * 4 > (size_t)max_smem) --dist;  // keep at least four warps per CTA
-    ly.dist = dist;
-    const size_t per_warp = Cfg::warp_bytes(dist + 1);
+    const size_t per_warp = Cfg::WARP_BYTES;
+    if (per_warp > (size_t)max_smem || blob > (size_t)max_smem) return p;
     int maxw = (int)std::min<size_t>(GPS_MAX_WARPS, (size_t)max_smem / per_warp);
     maxw = std::max(1, std::min(maxw, std::max(1, gps_env_int("TINYMPC_GPS_WARPS", GPS_MAX_WARPS))));
-    if (per_warp > (size_t)max_smem || blob > (size_t)max_smem) return p;
     // balance the waves: with `waves` passes over the resident slots, use just enough warps per SM to hold B / waves
-    const int64_t groups = (d.io.B + IPW - 1) / IPW;
+    const int64_t groups = (d.io.B + SPW - 1) / SPW;  // warps' worth of instances
     const int64_t cap = (int64_t)d.sm_count * maxw;
     const int64_t waves = std::max<int64_t>(1, (groups + cap - 1) / cap);
     int warps = (int)std::min<int64_t>(maxw, std::max<int64_t>(1, (groups + waves * d.sm_count - 1) / (waves * d.sm_count)));
     p.L = L;
+    p.NI = NI;
     p.warps = warps;
     p.ctas = (int)std::max<int64_t>(1, std::min<int64_t>(d.sm_count, (groups + warps - 1) / warps));
-    p.dist = dist;
     p.smem = std::max(per_warp * (size_t)warps, blob);
-    p.ws_bytes = (size_t)p.ctas * warps * d.N * ly.rec * sizeof(T);
+    p.ws_bytes = (size_t)p.ctas * warps * d.N * (REC::recA + (p.ly.has_b ? REC::recB : 0)) * sizeof(T);
     return p;
 }
 
-template <typename T, int NX, int NU, bool FAST, bool EXT>
+template <typename T, int NX, int NU, int L, int NI, int FAM, bool FAST>
+int launch_gps_cfg(LaunchDesc *d, const KParams<T, NX, NU> &P0) {
+    const GpsPlan plan = gps_plan_L<T, NX, NU, L, NI, FAM>(*d);
+    if (plan.L == 0 || !d->gmat || !d->work_queue) return TINYMPC_ERR_UNSUPPORTED;
+    d->out_ws_need = plan.ws_bytes;
+    if (!d->gps_ws || d->gps_ws_bytes < plan.ws_bytes) return TM_ERR_WORKSPACE;
+    KParams<T, NX, NU> P = P0;
+    P.gps = plan.ly;
+    P.gps_ws = (T *)d->gps_ws;
+    auto kern = gps_solve_kernel<T, NX, NU, L, NI, FAM, FAST>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem) != cudaSuccess) return TINYMPC_ERR_CUDA;
+    kern<<<plan.ctas, plan.warps * 32, plan.smem, d->stream>>>(P, (const T *)d->gmat, (unsigned long long *)d->work_queue);
+    d->out_threads = plan.warps * 32;
+    d->out_ctas = plan.ctas;
+    d->out_smem = (int)plan.smem;
+    d->out_lanes_per_instance = L;
+    d->out_instances_per_cta = plan.warps * (32 / L) * NI;
+    d->out_tmem_cols = 0;
+    return cudaGetLastError() == cudaSuccess ? TINYMPC_OK : TINYMPC_ERR_CUDA;
+}
+
+// family mask of the kernel that serves a feature set: 0 box only, 1 cones only, 6 hyperplanes only, 7 anything else
+inline int gps_family_mask(const LaunchDesc &d) {
+    const bool soc = d.soc_x || d.soc_u, lin = d.lin_x || d.lin_u || d.tvl_x || d.tvl_u;
+    return !soc && !lin ? 0 : (soc && !lin ? 1 : (!soc ? 6 : 7));
+}
+
+template <typename T, int NX, int NU, bool FAST>
 int launch_gps(LaunchDesc *d, const KParams<T, NX, NU> &P0) {
     constexpr int L = gps_pick_L<T, NX, NU>();
     if constexpr (L == 0) {
         return TINYMPC_ERR_UNSUPPORTED;
     } else {
-        const GpsPlan plan = gps_plan_L<T, NX, NU, L, EXT>(*d);
-        if (plan.L == 0 || !d->gmat || !d->work_queue) return TINYMPC_ERR_UNSUPPORTED;
-        d->out_ws_need = plan.ws_bytes;
-        if (!d->gps_ws || d->gps_ws_bytes < plan.ws_bytes) return TM_ERR_WORKSPACE;
-        KParams<T, NX, NU> P = P0;
-        P.gps = plan.ly;
-        P.gps_ws = (T *)d->gps_ws;
-        auto kern = gps_solve_kernel<T, NX, NU, L, FAST, EXT>;
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem) != cudaSuccess) return TINYMPC_ERR_CUDA;
-        kern<<<plan.ctas, plan.warps * 32, plan.smem, d->stream>>>(P, (const T *)d->gmat, (unsigned long long *)d->work_queue);
-        d->out_threads = plan.warps * 32;
-        d->out_ctas = plan.ctas;
-        d->out_smem = (int)plan.smem;
-        d->out_lanes_per_instance = L;
-        d->out_instances_per_cta = plan.warps * (32 / L);
-        d->out_tmem_cols = 0;
-        return cudaGetLastError() == cudaSuccess ? TINYMPC_OK : TINYMPC_ERR_CUDA;
+        constexpr int NIP = gps_pick_NI<T, NX, NU, L>();
+        const int fam = gps_family_mask(*d);
+        int ni = gps_env_int("TINYMPC_GPS_NI", NIP);
+        if (ni != 1 && ni != 2) ni = NIP;
+        if (ni > NIP) ni = NIP;
+#define TM_GPS_CASE(FF)                                                                   \
+    if (fam == FF) {                                                                      \
+        if constexpr (NIP == 2) {                                                         \
+            if (ni == 2) return launch_gps_cfg<T, NX, NU, L, 2, FF, FAST>(d, P0);         \
+        }                                                                                 \
+        return launch_gps_cfg<T, NX, NU, L, 1, FF, FAST>(d, P0);                          \
+    }
+        TM_GPS_CASE(0)
+        TM_GPS_CASE(1)
+        TM_GPS_CASE(6)
+        TM_GPS_CASE(7)
+#undef TM_GPS_CASE
+        return TINYMPC_ERR_UNSUPPORTED;
     }
 }
 

@@ -166,8 +166,7 @@ int launch_T(LaunchDesc *d) {
     if (d->io.models) return TINYMPC_ERR_UNSUPPORTED;
     KParams<T, TM_NX, TM_NU> P;
     fill_params<T, TM_NX, TM_NU>(P, *d);
-    if (d->ext) return d->fast ? launch_gps<T, TM_NX, TM_NU, true, true>(d, P) : launch_gps<T, TM_NX, TM_NU, false, true>(d, P);
-    return d->fast ? launch_gps<T, TM_NX, TM_NU, true, false>(d, P) : launch_gps<T, TM_NX, TM_NU, false, false>(d, P);
+    return d->fast ? launch_gps<T, TM_NX, TM_NU, true>(d, P) : launch_gps<T, TM_NX, TM_NU, false>(d, P);
 }
 
 }  // namespace

@@ -60,9 +60,14 @@ struct GpsCfg {
     static constexpr int PXB = 32 * RX * ES;  // bytes of one state-shaped piece slot (32 lanes, one instance of the group)
     static constexpr int PUB = 32 * RU * ES;
     static constexpr int STAGE_BYTES = NI * (XP * PXB + UP * PUB);
-    static constexpr int MAT_REGS = RX * (2 * NX + 2 * NU + 3) + RU * (2 * NX + NU + 2);
-    static constexpr bool ok = (NX % RX == 0) && (NU % RU == 0) && (MAT_REGS * (ES / 4) <= 150);
-    static constexpr size_t WARP_BYTES = (size_t)(GBX + GBU) * ES + (size_t)3 * STAGE_BYTES;  // 3 = GPS_STAGES
+    // matrix rows a lane holds in registers during one sweep (elements): forward A, Kinf, B, Qd, f, Rd; backward AmBKt,
+    // B^T, Kinf^T, Quu_inv, APf, BPf
+    static constexpr int FWD_ROWS = (RX + RU) * NX + RX * NU + 2 * RX + RU;
+    static constexpr int BWD_ROWS = (RX + RU) * NX + RX * NU + RU * NU + RX + RU;
+    static constexpr int SWEEP_REGS = (FWD_ROWS > BWD_ROWS ? FWD_ROWS : BWD_ROWS) * (ES / 4);
+    static constexpr bool ok = (NX % RX == 0) && (NU % RU == 0) && SWEEP_REGS <= 112;
+    static constexpr int PARK_BYTES = 32 * NI * 2 * RX * ES;  // per-lane x0 rows and terminal-cost rows (kept out of registers)
+    static constexpr size_t WARP_BYTES = (size_t)(GBX + GBU) * ES + (size_t)PARK_BYTES + (size_t)3 * STAGE_BYTES;  // 3 = GPS_STAGES
     // ring slot of family f's dual (f must be compiled in)
     __host__ __device__ static constexpr int fslot(int f) { return gps_popc(FAM & ((1 << f) - 1)); }
 };
@@ -98,7 +103,7 @@ constexpr int gps_pick_L() {
 // instances per lane group: two when the matrix rows leave room for a second set of working registers
 template <typename T, int NX, int NU, int L>
 constexpr int gps_pick_NI() {
-    return GpsCfg<NX, NU, L, (int)sizeof(T), 1, 0>::MAT_REGS * (int)(sizeof(T) / 4) <= 128 ? 2 : 1;
+    return GpsCfg<NX, NU, L, (int)sizeof(T), 1, 0>::SWEEP_REGS <= 72 ? 2 : 1;
 }
 
 constexpr int GPS_MAX_WARPS = 8;
@@ -253,49 +258,58 @@ __global__ void __launch_bounds__(GPS_MAX_WARPS * 32, 1)
         }
     }
     const bool xvl = l * RX < NX, uvl = l * RU < NU;  // does this lane own real rows (else padding rows: zeros)
-    T mS1b[RX + RU][NX], mS1f[RX + RU][NX];
-    T mKt[RX][NU], mB[RX][NU], vQd[RX], vAPf[RX], vf[RX];
-    T mQuu[RU][NU], vRd[RU], vBPf[RU];
-    {
-        const T *src = stage;
+    // The staged blob stays in shared memory for the whole kernel.  A sweep only needs half of the matrices (forward:
+    // A, Kinf, B; backward: AmBKt, B^T, Kinf^T, Quu_inv), so each sweep pulls this lane's rows of ITS matrices into
+    // registers when it starts: about half the register footprint of keeping everything resident, which is what makes
+    // room for the second instance per lane group.
+    const unsigned aBlob = (unsigned)__cvta_generic_to_shared(stage);
+    auto bl = [&](int idx) { return lds(aBlob + (unsigned)idx * ES, T()); };
+    auto load_fwd_rows = [&](T (&mS1f)[RX + RU][NX], T (&mB)[RX][NU], T (&vQd)[RX], T (&vf)[RX], T (&vRd)[RU]) {
 #pragma unroll
         for (int a = 0; a < RX; ++a) {
             const int ii = xvl ? l * RX + a : 0;
 #pragma unroll
-            for (int m = 0; m < NX; ++m) {
-                mS1b[a][m] = xvl ? src[OFF_AMBKT + ii + NX * m] : T(0);
-                mS1f[a][m] = xvl ? src[OFF_A + ii + NX * m] : T(0);
-            }
+            for (int m = 0; m < NX; ++m) mS1f[a][m] = xvl ? bl(OFF_A + ii + NX * m) : T(0);
 #pragma unroll
-            for (int j = 0; j < NU; ++j) {
-                mKt[a][j] = xvl ? src[OFF_K + j + NU * ii] : T(0);
-                mB[a][j] = xvl ? src[OFF_B + ii + NX * j] : T(0);
-            }
-            vQd[a] = xvl ? src[OFF_QD + ii] : T(0);
-            vAPf[a] = xvl ? src[OFF_APF + ii] : T(0);
-            vf[a] = xvl ? src[OFF_F + ii] : T(0);
+            for (int j = 0; j < NU; ++j) mB[a][j] = xvl ? bl(OFF_B + ii + NX * j) : T(0);
+            vQd[a] = xvl ? bl(OFF_QD + ii) : T(0);
+            vf[a] = xvl ? bl(OFF_F + ii) : T(0);
         }
 #pragma unroll
         for (int b = 0; b < RU; ++b) {
             const int jj = uvl ? l * RU + b : 0;
 #pragma unroll
-            for (int m = 0; m < NX; ++m) {
-                mS1b[RX + b][m] = uvl ? src[OFF_B + m + NX * jj] : T(0);
-                mS1f[RX + b][m] = uvl ? src[OFF_K + jj + NU * m] : T(0);
-            }
-#pragma unroll
-            for (int m = 0; m < NU; ++m) mQuu[b][m] = uvl ? src[OFF_QUU + jj + NU * m] : T(0);
-            vRd[b] = uvl ? src[OFF_RD + jj] : T(0);
-            vBPf[b] = uvl ? src[OFF_BPF + jj] : T(0);
+            for (int m = 0; m < NX; ++m) mS1f[RX + b][m] = uvl ? bl(OFF_K + jj + NU * m) : T(0);
+            vRd[b] = uvl ? bl(OFF_RD + jj) : T(0);
         }
-    }
-    __syncthreads();  // the staging area is reused below
+    };
+    auto load_bwd_rows = [&](T (&mS1b)[RX + RU][NX], T (&mKt)[RX][NU], T (&mQuu)[RU][NU], T (&vAPf)[RX], T (&vBPf)[RU]) {
+#pragma unroll
+        for (int a = 0; a < RX; ++a) {
+            const int ii = xvl ? l * RX + a : 0;
+#pragma unroll
+            for (int m = 0; m < NX; ++m) mS1b[a][m] = xvl ? bl(OFF_AMBKT + ii + NX * m) : T(0);
+#pragma unroll
+            for (int j = 0; j < NU; ++j) mKt[a][j] = xvl ? bl(OFF_K + j + NU * ii) : T(0);  // Kinf^T(i,j) = Kinf(j,i)
+            vAPf[a] = xvl ? bl(OFF_APF + ii) : T(0);
+        }
+#pragma unroll
+        for (int b = 0; b < RU; ++b) {
+            const int jj = uvl ? l * RU + b : 0;
+#pragma unroll
+            for (int m = 0; m < NX; ++m) mS1b[RX + b][m] = uvl ? bl(OFF_B + m + NX * jj) : T(0);  // B^T(j,m) = B(m,j)
+#pragma unroll
+            for (int m = 0; m < NU; ++m) mQuu[b][m] = uvl ? bl(OFF_QUU + jj + NU * m) : T(0);
+            vBPf[b] = uvl ? bl(OFF_BPF + jj) : T(0);
+        }
+    };
 
     // ---- shared memory of this warp: gather scratch (state vectors | input vectors) + cp.async ring (S stages) ----
     constexpr unsigned wbytes = (unsigned)Cfg::WARP_BYTES;
-    const unsigned aGX = (unsigned)__cvta_generic_to_shared(smem_raw) + (unsigned)warp * wbytes;
+    const unsigned aGX = aBlob + BLOB_BYTES + (unsigned)warp * wbytes;
     const unsigned aGU = aGX + (unsigned)Cfg::GBX * ES;
-    const unsigned aRing = aGU + (unsigned)Cfg::GBU * ES;
+    const unsigned aPark = aGU + (unsigned)Cfg::GBU * ES + (unsigned)lane * (NI * 2 * RX) * ES;  // [j][x0 rows | pterm rows]
+    const unsigned aRing = aGU + (unsigned)Cfg::GBU * ES + (unsigned)Cfg::PARK_BYTES;
     const unsigned aXl = aRing + (unsigned)lane * RX * ES;        // + stage offset + (piece*NI + j)*PXB
     const unsigned aUl = aRing + XPB + (unsigned)lane * RU * ES;  // + stage offset + (piece*NI + j)*PUB
     // padding lanes never receive data: their ring slices stay zero
@@ -381,21 +395,28 @@ __global__ void __launch_bounds__(GPS_MAX_WARPS * 32, 1)
     int64_t inst[NI];
     bool busy[NI], want[NI];
     int it[NI], solved[NI];
-    T res_px[NI], res_dx[NI], res_pu[NI], res_du[NI];
-    T x0o[NI][RX], pterm[NI][RX];
-    const T *xrefp[NI], *urefp[NI];
 #pragma unroll
     for (int j = 0; j < NI; ++j) {
         inst[j] = -1;
         busy[j] = false;
         want[j] = true;
         it[j] = solved[j] = 0;
-        res_px[j] = res_dx[j] = res_pu[j] = res_du[j] = T(0);
-#pragma unroll
-        for (int a = 0; a < RX; ++a) x0o[j][a] = pterm[j][a] = T(0);
-        xrefp[j] = P.Xref + l * RX;
-        urefp[j] = has_uref ? P.Uref + l * RU : P.Xref;
+        const T z[RX] = {};
+        sts_piece<T, RX, SX>(aPark + (unsigned)((2 * j) * RX) * ES, z);
+        sts_piece<T, RX, SX>(aPark + (unsigned)((2 * j + 1) * RX) * ES, z);
     }
+    // x0 rows / terminal-cost rows of instance j of this lane's group: parked in shared memory, fetched where used
+    auto load_x0 = [&](int j, T (&v)[RX]) { lds_piece<T, RX, SX>(aPark + (unsigned)((2 * j) * RX) * ES, v); };
+    auto load_pterm = [&](int j, T (&v)[RX]) { lds_piece<T, RX, SX>(aPark + (unsigned)((2 * j + 1) * RX) * ES, v); };
+    // reference columns of instance j (this lane's rows of column 0); instances outside the batch read instance 0's
+    auto xref_of = [&](int j) {
+        const int64_t ib = inst[j] < 0 ? 0 : inst[j];
+        return P.Xref + (P.xref_pi ? ib * (int64_t)N * NX : 0) + l * RX;
+    };
+    auto uref_of = [&](int j) {
+        const int64_t ib = inst[j] < 0 ? 0 : inst[j];
+        return has_uref ? P.Uref + (P.uref_pi ? ib * (int64_t)(N - 1) * NU : 0) + l * RU : P.Xref;
+    };
 
     // ---- cone projections of one knot point (admm.cpp:102-135).  The candidate slacks (x + gc, u + yc; own rows) of the
     // group's NI instances go to the gather scratch; the 2*NI (instance, side) vectors are work items dealt to the
@@ -569,14 +590,15 @@ __global__ void __launch_bounds__(GPS_MAX_WARPS * 32, 1)
     // ---- forward sweep: rollout (admm.cpp:25-32) fused with update_slack (:81-213), update_dual (:219-256), the
     // residual maxima of termination_condition (:310-328) and the NEXT iteration's update_linear_cost (:262-304) ----
     auto forward = [&](T (&rpx)[NI], T (&rdx)[NI], T (&rpu)[NI], T (&rdu)[NI]) {
+        T mS1f[RX + RU][NX], mB[RX][NU], vQd[RX], vf[RX], vRd[RU];
+        load_fwd_rows(mS1f, mB, vQd, vf, vRd);
         T xo[NI][RX], Xf[NI][NX];
         const T *xr[NI], *ur[NI];  // reference columns of the knot point D steps ahead (what the next issue fetches)
 #pragma unroll
         for (int j = 0; j < NI; ++j) {
-#pragma unroll
-            for (int a = 0; a < RX; ++a) xo[j][a] = x0o[j][a];
-            xr[j] = xrefp[j];
-            ur[j] = urefp[j];
+            load_x0(j, xo[j]);
+            xr[j] = xref_of(j);
+            ur[j] = uref_of(j);
         }
         T *cx = px0, *cu = pu0;  // this lane's rows in the record of the CURRENT knot point
 #pragma unroll
@@ -629,10 +651,11 @@ __global__ void __launch_bounds__(GPS_MAX_WARPS * 32, 1)
             T q[NI][RX], r[NI][RU];
 #pragma unroll
             for (int j = 0; j < NI; ++j) {
-                T vo[RX], g[RX], xrf[RX], vn[RX], gn[RX];
+                T vo[RX], g[RX], xrf[RX], vn[RX], gn[RX], pt[RX];
                 lds_piece<T, RX, SX>(bx + (0 * NI + j) * PXB, vo);
                 lds_piece<T, RX, SX>(bx + (1 * NI + j) * PXB, g);
                 lds_piece<T, RX, SX>(bx + (2 * NI + j) * PXB, xrf);
+                if (!HASU) load_pterm(j, pt);
 #pragma unroll
                 for (int a = 0; a < RX; ++a) {
                     const T v = clamp_box<FAST>(xo[j][a] + g[a], loX[a], hiX[a]);  // vnew = clamp(x + g)
@@ -641,7 +664,7 @@ __global__ void __launch_bounds__(GPS_MAX_WARPS * 32, 1)
                     rpx[j] = absmax(rpx[j], xo[j][a] - v);
                     rdx[j] = absmax(rdx[j], vo[a] - v);
                     // k < N-1: q_k = -(xref*Q) - rho (vnew - g);  k = N-1: p_{N-1} = -(Pinf^T xref) - rho (vnew - g)
-                    const T base = HASU ? -(xrf[a] * vQd[a]) : pterm[j][a];
+                    const T base = HASU ? -(xrf[a] * vQd[a]) : pt[a];
                     q[j][a] = nmac<FAST>(base, rho, v - gn[a]);
                 }
                 if (xvl) {
@@ -751,6 +774,8 @@ __global__ void __launch_bounds__(GPS_MAX_WARPS * 32, 1)
 
     // ---- backward sweep (admm.cpp:13-20) on the stored linear cost ----
     auto backward = [&]() {
+        T mS1b[RX + RU][NX], mKt[RX][NU], mQuu[RU][NU], vAPf[RX], vBPf[RU];
+        load_bwd_rows(mS1b, mKt, mQuu, vAPf, vBPf);
         T *cx = px0 + (int64_t)(N - 1) * recA, *cu = pu0 + (int64_t)(N - 1) * recA;  // record of the current knot point
 #pragma unroll
         for (int t = 0; t < D; ++t) issue_bwd(N - 1 - t, (unsigned)t * STAGE, cx - t * recA, cu - t * recA);
@@ -882,17 +907,22 @@ __global__ void __launch_bounds__(GPS_MAX_WARPS * 32, 1)
             busy[J] = true;
             it[J] = 0;
             solved[J] = 0;
-            res_px[J] = res_dx[J] = res_pu[J] = res_du[J] = T(0);
-            xrefp[J] = xrefb + l * RX;
-            urefp[J] = has_uref ? urefb + l * RU : P.Xref;
             const T *xl = xrefb + (int64_t)(N - 1) * NX;
+            T x0v[RX], ptv[RX];
 #pragma unroll
             for (int a = 0; a < RX; ++a) {
                 const int ii = xvl ? l * RX + a : 0;
-                x0o[J][a] = xvl ? __ldg(P.x0 + ib * NX + ii) : T(0);
+                x0v[a] = xvl ? __ldg(P.x0 + ib * NX + ii) : T(0);
                 T sacc = __ldg(xl) * __ldg(gmat + OFF_PINF + NX * ii);
                 for (int m = 1; m < NX; ++m) sacc = mac<FAST>(sacc, __ldg(xl + m), __ldg(gmat + OFF_PINF + m + NX * ii));
-                pterm[J][a] = xvl ? -sacc : T(0);
+                ptv[a] = xvl ? -sacc : T(0);
+            }
+            sts_piece<T, RX, SX>(aPark + (unsigned)((2 * J) * RX) * ES, x0v);
+            sts_piece<T, RX, SX>(aPark + (unsigned)((2 * J + 1) * RX) * ES, ptv);
+            // the four residuals keep their last checked value (types.hpp:202-205); none checked yet
+            if (l == 0 && P.residuals) {
+                T *r4 = P.residuals + 4 * ib;
+                r4[0] = r4[1] = r4[2] = r4[3] = T(0);
             }
         }
         __syncwarp();  // the records were written by all lanes; their owners read them from here on
@@ -907,10 +937,6 @@ __global__ void __launch_bounds__(GPS_MAX_WARPS * 32, 1)
         if (grp == s && l == 0) {
             if (P.iter) P.iter[ib] = it[J];
             if (P.solved) P.solved[ib] = solved[J];
-            if (P.residuals) {
-                T *r = P.residuals + 4 * ib;
-                r[0] = res_px[J]; r[1] = res_dx[J]; r[2] = res_pu[J]; r[3] = res_du[J];
-            }
         }
         __syncwarp();  // owner lanes wrote the records; every lane reads them below
         const int64_t ox = ib * (int64_t)N * NX, ou = ib * (int64_t)(N - 1) * NU;
@@ -966,11 +992,11 @@ __global__ void __launch_bounds__(GPS_MAX_WARPS * 32, 1)
         if (P.s_x || P.s_u || P.u0) {
             __syncwarp();
             const bool mine = grp == s;
+            T mS1f[RX + RU][NX], mB[RX][NU], vQd[RX], vf[RX], vRd[RU];
+            load_fwd_rows(mS1f, mB, vQd, vf, vRd);
             T xo[NI][RX], Xf[NI][NX];
 #pragma unroll
-            for (int j = 0; j < NI; ++j)
-#pragma unroll
-                for (int a = 0; a < RX; ++a) xo[j][a] = x0o[j][a];
+            for (int j = 0; j < NI; ++j) load_x0(j, xo[j]);
             gather_x(xo, Xf);
             const int kend = (P.s_x || P.s_u) ? N : 1;
             for (int k = 0; k < kend; ++k) {
@@ -1073,11 +1099,12 @@ __global__ void __launch_bounds__(GPS_MAX_WARPS * 32, 1)
                 if (busy[j]) {
                     it[j] += 1;
                     if (it[j] % P.check_termination == 0) {
-                        res_px[j] = a;
-                        res_dx[j] = b * rho;
-                        res_pu[j] = c;
-                        res_du[j] = d * rho;
-                        if (res_px[j] < P.pri_tol && res_pu[j] < P.pri_tol && res_dx[j] < P.dua_tol && res_du[j] < P.dua_tol) solved[j] = 1;
+                        const T r_px = a, r_dx = b * rho, r_pu = c, r_du = d * rho;
+                        if (l == 0 && P.residuals) {
+                            T *r4 = P.residuals + 4 * inst[j];
+                            r4[0] = r_px; r4[1] = r_dx; r4[2] = r_pu; r4[3] = r_du;
+                        }
+                        if (r_px < P.pri_tol && r_pu < P.pri_tol && r_dx < P.dua_tol && r_du < P.dua_tol) solved[j] = 1;
                     }
                 }
                 stop = stop || (busy[j] && (solved[j] || it[j] >= P.max_iter));
@@ -1110,10 +1137,10 @@ inline GpsPlan gps_plan_L(const LaunchDesc &d) {
     // region B: previous box slacks (work->v / work->z) and family slacks, only when the caller wants them back
     p.ly.has_b = (s.v || s.z || s.vcnew || s.zcnew || s.vlnew || s.zlnew || s.vlnew_tv || s.zlnew_tv) ? 1 : 0;
     const int max_smem = d.max_smem_optin - 64;
-    const size_t blob = ((size_t)(3 * NX * NX + 2 * NX * NU + NU * NU + 4 * NX + 2 * NU) * sizeof(T) + 15) / 16 * 16 + 64;
+    const size_t blob = ((size_t)(3 * NX * NX + 2 * NX * NU + NU * NU + 4 * NX + 2 * NU) * sizeof(T) + 15) / 16 * 16;
     const size_t per_warp = Cfg::WARP_BYTES;
-    if (per_warp > (size_t)max_smem || blob > (size_t)max_smem) return p;
-    int maxw = (int)std::min<size_t>(GPS_MAX_WARPS, (size_t)max_smem / per_warp);
+    if (blob + per_warp > (size_t)max_smem) return p;
+    int maxw = (int)std::min<size_t>(GPS_MAX_WARPS, ((size_t)max_smem - blob) / per_warp);
     maxw = std::max(1, std::min(maxw, std::max(1, gps_env_int("TINYMPC_GPS_WARPS", GPS_MAX_WARPS))));
     // balance the waves: with `waves` passes over the resident slots, use just enough warps per SM to hold B / waves
     const int64_t groups = (d.io.B + SPW - 1) / SPW;  // warps' worth of instances
@@ -1124,7 +1151,7 @@ inline GpsPlan gps_plan_L(const LaunchDesc &d) {
     p.NI = NI;
     p.warps = warps;
     p.ctas = (int)std::max<int64_t>(1, std::min<int64_t>(d.sm_count, (groups + warps - 1) / warps));
-    p.smem = std::max(per_warp * (size_t)warps, blob);
+    p.smem = blob + per_warp * (size_t)warps;
     p.ws_bytes = (size_t)p.ctas * warps * d.N * (REC::recA + (p.ly.has_b ? REC::recB : 0)) * sizeof(T);
     return p;
 }

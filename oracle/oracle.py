@@ -142,3 +142,45 @@ def solve_batch(prob: MPCProblem, settings: abi.Settings | None, x0, Xref, Uref=
     if rc:
         raise RuntimeError(f"{impl} solve_batch rc={rc}")
     return hb.result()
+
+
+class RefPool:
+    """Persistent worker pool around the compiled reference (oracle/ref_driver.cpp: tinympc_ref_pool_*): `nthreads` threads,
+    one TinySolver per thread built ONCE through the reference's tiny_setup; used by bench.py's CPU arm so that thread
+    spawn and setup stay outside the timed region."""
+
+    def __init__(self, prob: MPCProblem, settings: abi.Settings | None, nthreads: int, variant=""):
+        self.prob = prob
+        self.lib = ref_lib(prob.dtype, variant)
+        self.lib.tinympc_ref_pool_create.restype = C.c_void_p
+        self.lib.tinympc_ref_pool_create.argtypes = [C.POINTER(abi.Problem), C.POINTER(abi.Settings), C.c_int32]
+        self.lib.tinympc_ref_pool_solve.restype = C.c_int
+        self.lib.tinympc_ref_pool_solve.argtypes = [C.c_void_p, C.POINTER(abi.Batch), C.c_int32, C.POINTER(C.c_double)]
+        self.lib.tinympc_ref_pool_destroy.restype = None
+        self.lib.tinympc_ref_pool_destroy.argtypes = [C.c_void_p]
+        st = settings if settings is not None else default_settings()
+        cp = prob.to_c()
+        self.nthreads = int(nthreads)
+        self.h = self.lib.tinympc_ref_pool_create(C.byref(cp), C.byref(st), self.nthreads)
+        if not self.h:
+            raise RuntimeError("tinympc_ref_pool_create failed")
+
+    def solve(self, hb: HostBatch, chunk=16):
+        """One batched tiny_solve of `hb` on the pool; returns the wall seconds measured inside the driver."""
+        cb = hb.to_c()
+        sec = C.c_double(0.0)
+        rc = self.lib.tinympc_ref_pool_solve(self.h, C.byref(cb), chunk, C.byref(sec))
+        if rc:
+            raise RuntimeError(f"tinympc_ref_pool_solve rc={rc}")
+        return sec.value
+
+    def close(self):
+        if self.h:
+            self.lib.tinympc_ref_pool_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

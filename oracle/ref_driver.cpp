@@ -13,9 +13,14 @@
 //
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may load this.
 
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
 #include <cstdint>
 #include <cstring>
 #include <iostream>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -112,6 +117,75 @@ void free_solver(TinySolver *s) {  // the reference has no destroy function (SUR
     delete s;
 }
 
+// One tiny_solve of instance b of `io` on solver `s` (pokes per examples/quadrotor_tracking.cpp:86-97).
+void solve_instance(TinySolver *s, const tinympc_problem_t *pr, const tinympc_batch_t *io, int64_t b) {
+    const int nx = pr->nx, nu = pr->nu, N = pr->N;
+    TinyWorkspace *w = s->work;
+    const tinympc_state_t &S = io->state;
+    const bool cold = io->cold_start != 0;
+    load(w->x, cold ? nullptr : S.x, b, nx, N);
+    load(w->u, cold ? nullptr : S.u, b, nu, N - 1);
+    load(w->v, cold ? nullptr : S.v, b, nx, N);
+    load(w->z, cold ? nullptr : S.z, b, nu, N - 1);
+    load(w->vnew, cold ? nullptr : S.vnew, b, nx, N);
+    load(w->znew, cold ? nullptr : S.znew, b, nu, N - 1);
+    load(w->g, cold ? nullptr : S.g, b, nx, N);
+    load(w->y, cold ? nullptr : S.y, b, nu, N - 1);
+    load(w->vcnew, cold ? nullptr : S.vcnew, b, nx, N);
+    load(w->zcnew, cold ? nullptr : S.zcnew, b, nu, N - 1);
+    load(w->gc, cold ? nullptr : S.gc, b, nx, N);
+    load(w->yc, cold ? nullptr : S.yc, b, nu, N - 1);
+    load(w->vlnew, cold ? nullptr : S.vlnew, b, nx, N);
+    load(w->zlnew, cold ? nullptr : S.zlnew, b, nu, N - 1);
+    load(w->gl, cold ? nullptr : S.gl, b, nx, N);
+    load(w->yl, cold ? nullptr : S.yl, b, nu, N - 1);
+    load(w->vlnew_tv, cold ? nullptr : S.vlnew_tv, b, nx, N);
+    load(w->zlnew_tv, cold ? nullptr : S.zlnew_tv, b, nu, N - 1);
+    load(w->gl_tv, cold ? nullptr : S.gl_tv, b, nx, N);
+    load(w->yl_tv, cold ? nullptr : S.yl_tv, b, nu, N - 1);
+    load(w->Xref, io->Xref, io->xref_per_instance ? b : 0, nx, N);
+    load(w->Uref, io->Uref, io->uref_per_instance ? b : 0, nu, N - 1);
+    w->primal_residual_state = 0;
+    w->dual_residual_state = 0;
+    w->primal_residual_input = 0;
+    w->dual_residual_input = 0;
+    tiny_set_x0(s, map_vec(static_cast<const T *>(io->x0) + b * nx, nx));
+
+    tiny_solve(s);
+
+    store(io->sol_x, b, s->solution->x);
+    store(io->sol_u, b, s->solution->u);
+    if (io->iter) io->iter[b] = s->solution->iter;
+    if (io->solved) io->solved[b] = s->solution->solved;
+    if (io->residuals) {
+        T *r = static_cast<T *>(io->residuals) + 4 * b;
+        r[0] = w->primal_residual_state;
+        r[1] = w->dual_residual_state;
+        r[2] = w->primal_residual_input;
+        r[3] = w->dual_residual_input;
+    }
+    store(S.x, b, w->x);
+    store(S.u, b, w->u);
+    store(S.v, b, w->v);
+    store(S.z, b, w->z);
+    store(S.vnew, b, w->vnew);
+    store(S.znew, b, w->znew);
+    store(S.g, b, w->g);
+    store(S.y, b, w->y);
+    store(S.vcnew, b, w->vcnew);
+    store(S.zcnew, b, w->zcnew);
+    store(S.gc, b, w->gc);
+    store(S.yc, b, w->yc);
+    store(S.vlnew, b, w->vlnew);
+    store(S.zlnew, b, w->zlnew);
+    store(S.gl, b, w->gl);
+    store(S.yl, b, w->yl);
+    store(S.vlnew_tv, b, w->vlnew_tv);
+    store(S.zlnew_tv, b, w->zlnew_tv);
+    store(S.gl_tv, b, w->gl_tv);
+    store(S.yl_tv, b, w->yl_tv);
+}
+
 void run_range(const tinympc_problem_t *pr, const tinympc_settings_t *st, const tinympc_batch_t *io, int64_t b0,
                int64_t b1, int *rc) {
     TinySolver *s = make_solver(pr, st);
@@ -119,76 +193,64 @@ void run_range(const tinympc_problem_t *pr, const tinympc_settings_t *st, const 
         *rc = -1;
         return;
     }
-    const int nx = pr->nx, nu = pr->nu, N = pr->N;
-    TinyWorkspace *w = s->work;
-    const tinympc_state_t &S = io->state;
-    const bool cold = io->cold_start != 0;
-    for (int64_t b = b0; b < b1; ++b) {
-        load(w->x, cold ? nullptr : S.x, b, nx, N);
-        load(w->u, cold ? nullptr : S.u, b, nu, N - 1);
-        load(w->v, cold ? nullptr : S.v, b, nx, N);
-        load(w->z, cold ? nullptr : S.z, b, nu, N - 1);
-        load(w->vnew, cold ? nullptr : S.vnew, b, nx, N);
-        load(w->znew, cold ? nullptr : S.znew, b, nu, N - 1);
-        load(w->g, cold ? nullptr : S.g, b, nx, N);
-        load(w->y, cold ? nullptr : S.y, b, nu, N - 1);
-        load(w->vcnew, cold ? nullptr : S.vcnew, b, nx, N);
-        load(w->zcnew, cold ? nullptr : S.zcnew, b, nu, N - 1);
-        load(w->gc, cold ? nullptr : S.gc, b, nx, N);
-        load(w->yc, cold ? nullptr : S.yc, b, nu, N - 1);
-        load(w->vlnew, cold ? nullptr : S.vlnew, b, nx, N);
-        load(w->zlnew, cold ? nullptr : S.zlnew, b, nu, N - 1);
-        load(w->gl, cold ? nullptr : S.gl, b, nx, N);
-        load(w->yl, cold ? nullptr : S.yl, b, nu, N - 1);
-        load(w->vlnew_tv, cold ? nullptr : S.vlnew_tv, b, nx, N);
-        load(w->zlnew_tv, cold ? nullptr : S.zlnew_tv, b, nu, N - 1);
-        load(w->gl_tv, cold ? nullptr : S.gl_tv, b, nx, N);
-        load(w->yl_tv, cold ? nullptr : S.yl_tv, b, nu, N - 1);
-        load(w->Xref, io->Xref, io->xref_per_instance ? b : 0, nx, N);
-        load(w->Uref, io->Uref, io->uref_per_instance ? b : 0, nu, N - 1);
-        w->primal_residual_state = 0;
-        w->dual_residual_state = 0;
-        w->primal_residual_input = 0;
-        w->dual_residual_input = 0;
-        tiny_set_x0(s, map_vec(static_cast<const T *>(io->x0) + b * nx, nx));
-
-        tiny_solve(s);
-
-        store(io->sol_x, b, s->solution->x);
-        store(io->sol_u, b, s->solution->u);
-        if (io->iter) io->iter[b] = s->solution->iter;
-        if (io->solved) io->solved[b] = s->solution->solved;
-        if (io->residuals) {
-            T *r = static_cast<T *>(io->residuals) + 4 * b;
-            r[0] = w->primal_residual_state;
-            r[1] = w->dual_residual_state;
-            r[2] = w->primal_residual_input;
-            r[3] = w->dual_residual_input;
-        }
-        store(S.x, b, w->x);
-        store(S.u, b, w->u);
-        store(S.v, b, w->v);
-        store(S.z, b, w->z);
-        store(S.vnew, b, w->vnew);
-        store(S.znew, b, w->znew);
-        store(S.g, b, w->g);
-        store(S.y, b, w->y);
-        store(S.vcnew, b, w->vcnew);
-        store(S.zcnew, b, w->zcnew);
-        store(S.gc, b, w->gc);
-        store(S.yc, b, w->yc);
-        store(S.vlnew, b, w->vlnew);
-        store(S.zlnew, b, w->zlnew);
-        store(S.gl, b, w->gl);
-        store(S.yl, b, w->yl);
-        store(S.vlnew_tv, b, w->vlnew_tv);
-        store(S.zlnew_tv, b, w->zlnew_tv);
-        store(S.gl_tv, b, w->gl_tv);
-        store(S.yl_tv, b, w->yl_tv);
-    }
+    for (int64_t b = b0; b < b1; ++b) solve_instance(s, pr, io, b);
     free_solver(s);
     *rc = 0;
 }
+
+// Persistent worker pool for the timing arm (bench.py --impl reference / cpu_baseline): `nthreads` std::threads, each with
+// ONE TinySolver built once through the reference's own tiny_setup, parked on a condition variable
+// between batches; a batch is handed out in chunks from an atomic counter so that a descheduled thread does not hold
+// the others back.
+struct Pool {
+    tinympc_problem_t pr;  // dims / counts only are read after construction
+    std::vector<std::thread> threads;
+    std::vector<TinySolver *> solvers;
+    std::mutex m;
+    std::condition_variable cv_work, cv_done;
+    const tinympc_batch_t *job = nullptr;
+    std::atomic<int64_t> next{0};
+    int64_t chunk = 16;
+    uint64_t generation = 0;
+    int running = 0, ready = 0;
+    bool stop = false, failed = false;
+
+    void worker(int t, const tinympc_problem_t *pr0, const tinympc_settings_t *st0) {
+        TinySolver *s = make_solver(pr0, st0);
+        {
+            std::lock_guard<std::mutex> lk(m);
+            solvers[t] = s;
+            failed |= (s == nullptr);
+            ++ready;
+        }
+        cv_done.notify_all();
+        uint64_t seen = 0;
+        for (;;) {
+            const tinympc_batch_t *io;
+            {
+                std::unique_lock<std::mutex> lk(m);
+                cv_work.wait(lk, [&] { return stop || generation != seen; });
+                if (stop) break;
+                seen = generation;
+                io = job;
+            }
+            if (s) {
+                for (;;) {
+                    int64_t b0 = next.fetch_add(chunk);
+                    if (b0 >= io->B) break;
+                    int64_t b1 = std::min<int64_t>(io->B, b0 + chunk);
+                    for (int64_t b = b0; b < b1; ++b) solve_instance(s, &pr, io, b);
+                }
+            }
+            {
+                std::lock_guard<std::mutex> lk(m);
+                --running;
+            }
+            cv_done.notify_all();
+        }
+        free_solver(s);
+    }
+};
 
 }  // namespace
 
@@ -251,6 +313,63 @@ int tinympc_ref_solve_batch(const tinympc_problem_t *pr, const tinympc_settings_
     for (int r : rcs)
         if (r) return r;
     return 0;
+}
+
+// ---- persistent pool (timing arm) ----
+void *tinympc_ref_pool_create(const tinympc_problem_t *pr, const tinympc_settings_t *st, int32_t nthreads) {
+    if (!pr || !st || pr->dtype != tinympc_ref_dtype()) return nullptr;
+    if (nthreads < 1) nthreads = 1;
+    std::ios_base::iostate old = std::cout.rdstate();
+    std::cout.setstate(std::ios_base::failbit);
+    Pool *p = new Pool;
+    p->pr = *pr;
+    p->solvers.assign(nthreads, nullptr);
+    for (int t = 0; t < nthreads; ++t) p->threads.emplace_back(&Pool::worker, p, t, pr, st);
+    {
+        std::unique_lock<std::mutex> lk(p->m);
+        p->cv_done.wait(lk, [&] { return p->ready == nthreads; });
+    }
+    std::cout.clear(old);
+    return p;
+}
+
+// One batched tiny_solve on the pool; `chunk` instances are handed to a thread at a time.  Returns seconds of wall time
+// (steady_clock around hand-out .. last thread done) through *seconds.
+int tinympc_ref_pool_solve(void *pool, const tinympc_batch_t *io, int32_t chunk, double *seconds) {
+    Pool *p = static_cast<Pool *>(pool);
+    if (!p || !io || !io->x0 || !io->Xref || p->failed) return -1;
+    std::ios_base::iostate old = std::cout.rdstate();
+    std::cout.setstate(std::ios_base::failbit);
+    auto t0 = std::chrono::steady_clock::now();
+    {
+        std::lock_guard<std::mutex> lk(p->m);
+        p->job = io;
+        p->chunk = chunk > 0 ? chunk : 16;
+        p->next.store(0);
+        p->running = (int)p->threads.size();
+        ++p->generation;
+    }
+    p->cv_work.notify_all();
+    {
+        std::unique_lock<std::mutex> lk(p->m);
+        p->cv_done.wait(lk, [&] { return p->running == 0; });
+    }
+    auto t1 = std::chrono::steady_clock::now();
+    std::cout.clear(old);
+    if (seconds) *seconds = std::chrono::duration<double>(t1 - t0).count();
+    return 0;
+}
+
+void tinympc_ref_pool_destroy(void *pool) {
+    Pool *p = static_cast<Pool *>(pool);
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> lk(p->m);
+        p->stop = true;
+    }
+    p->cv_work.notify_all();
+    for (auto &t : p->threads) t.join();
+    delete p;
 }
 
 }  // extern "C"

@@ -115,17 +115,25 @@ def tracking_instances(B, N=50, seed=0, dtype=np.float32, jitter=0.05):
     return dict(x0=x0, Xref=Xref, Uref=None)
 
 
-def rocket_instances(B, N=100, seed=0, dtype=np.float64, spread=0.1, step=0):
+def rocket_instances(B, N=100, seed=0, dtype=np.float64, spread=0.1, step=0, per_instance_refs=False):
     """C4: x0 = 1.1*xinit*(1 +- spread) per instance, Xref = linear interpolation to the origin over NTOTAL=100
-    (rocket_landing_mpc.cpp:104-135), Uref[2] = 10."""
+    (rocket_landing_mpc.cpp:104-135), Uref[2] = 10.  per_instance_refs: every instance sits at its own closed-loop step
+    (uniform in 0..20, the `k` of rocket_landing_mpc.cpp:131-135) and gets its own Xref window and Uref copy
+    ([B][N][nx] / [B][N-1][nu], the 14 440 B/instance case of SURVEY §8d)."""
     xinit = np.array([4, 2, 20, -3, 2, -4.5], dtype=np.float64)
     rng = np.random.default_rng(seed)
     x0 = 1.1 * xinit[None, :] * (1.0 + spread * rng.uniform(-1, 1, size=(B, 6)))
     ntotal = 100
-    k = (np.arange(N) + step)[:, None]
-    Xref = xinit[None, :] + (0.0 - xinit[None, :]) * k / (ntotal - 1)
     Uref = np.zeros((N - 1, 3))
     Uref[:, 2] = 10.0
+    if per_instance_refs:
+        steps = rng.integers(0, 21, size=B)
+        k = (np.arange(N)[None, :] + steps[:, None])[:, :, None]  # (B, N, 1)
+        Xref = xinit[None, None, :] + (0.0 - xinit[None, None, :]) * k / (ntotal - 1)
+        Uref = np.broadcast_to(Uref[None], (B, N - 1, 3))
+        return dict(x0=x0.astype(dtype), Xref=np.ascontiguousarray(Xref, dtype=dtype), Uref=np.ascontiguousarray(Uref, dtype=dtype))
+    k = (np.arange(N) + step)[:, None]
+    Xref = xinit[None, :] + (0.0 - xinit[None, :]) * k / (ntotal - 1)
     return dict(x0=x0.astype(dtype), Xref=Xref.astype(dtype), Uref=Uref.astype(dtype))
 
 

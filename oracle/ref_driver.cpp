@@ -315,6 +315,33 @@ int tinympc_ref_solve_batch(const tinympc_problem_t *pr, const tinympc_settings_
     return 0;
 }
 
+// The reference's tiny_initialize_sensitivity_matrices (tiny_api.cpp:479-540; quadrotor-sized hard-coded tables) run on a
+// freshly set-up 12 x 4 solver; the four d*_drho matrices are copied out column-major (4x12, 12x12, 4x4, 12x12).  Source of
+// the shim's table data (tools/extract_sensitivity_tables.py) and of the test that pins it.
+int tinympc_ref_sensitivity_tables(void *dKinf, void *dPinf, void *dC1, void *dC2) {
+    const int nx = 12, nu = 4, N = 3;
+    std::ios_base::iostate old = std::cout.rdstate();
+    std::cout.setstate(std::ios_base::failbit);
+    TinySolver *s = nullptr;
+    tinyMatrix A = tinyMatrix::Identity(nx, nx), B = tinyMatrix::Zero(nx, nu), Q = tinyMatrix::Identity(nx, nx),
+               R = tinyMatrix::Identity(nu, nu);
+    for (int j = 0; j < nu; ++j) B(j, j) = 1;
+    tinyVector f = tinyVector::Zero(nx);
+    int status = tiny_setup(&s, A, B, f, Q, R, (T)1, nx, nu, N, 0);
+    if (status || !s) {
+        std::cout.clear(old);
+        return -1;
+    }
+    tiny_initialize_sensitivity_matrices(s);
+    std::cout.clear(old);
+    std::memcpy(dKinf, s->cache->dKinf_drho.data(), sizeof(T) * nu * nx);
+    std::memcpy(dPinf, s->cache->dPinf_drho.data(), sizeof(T) * nx * nx);
+    std::memcpy(dC1, s->cache->dC1_drho.data(), sizeof(T) * nu * nu);
+    std::memcpy(dC2, s->cache->dC2_drho.data(), sizeof(T) * nx * nx);
+    free_solver(s);
+    return 0;
+}
+
 // ---- persistent pool (timing arm) ----
 void *tinympc_ref_pool_create(const tinympc_problem_t *pr, const tinympc_settings_t *st, int32_t nthreads) {
     if (!pr || !st || pr->dtype != tinympc_ref_dtype()) return nullptr;

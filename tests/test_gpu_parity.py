@@ -469,3 +469,137 @@ def test_device_precompute_bit_identical_to_host_precompute(dt, dims):
     assert H.bits_equal(dev.cpu().numpy(), host)
     sw = sweeps.cpu().numpy()
     assert (sw > 1).all() and (sw <= 1000).all() and len(set(sw.tolist())) > 1
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# launch plans of the on-chip kernel: every compiled (nx, nu) at the horizons of the BASELINE sweep (N = 50, 100), so that
+# each distinct (lanes per instance, instances per SM, tensor memory) plan of profiles/*_sweep_1gpu.md meets the oracle
+# ---------------------------------------------------------------------------------------------------------------------
+ALL_DIMS = [(4, 1), (6, 3), (12, 4), (4, 2), (4, 4), (4, 8), (8, 2), (8, 4), (8, 8), (12, 2), (12, 8), (16, 2), (16, 4), (16, 8)]
+# fp32 plans as measured in the round-1 sweep table: (lanes per instance, instances per SM, tensor-memory columns > 0)
+_P50 = {(4, 2): (4, 64, True), (4, 4): (4, 64, True), (8, 2): (4, 64, True), (8, 4): (4, 64, True), (12, 2): (4, 64, True),
+        (12, 4): (4, 64, True), (4, 8): (4, 32, True), (8, 8): (4, 32, True), (12, 8): (8, 32, True), (16, 2): (8, 32, True),
+        (16, 4): (8, 32, True), (16, 8): (8, 32, True)}
+_P100 = {(4, 2): (4, 32, True), (4, 4): (4, 32, True), (8, 2): (4, 32, True), (8, 4): (4, 32, True), (12, 2): (4, 32, True),
+         (12, 4): (4, 32, True), (4, 8): (8, 16, True), (8, 8): (8, 16, True), (12, 8): (8, 16, True), (16, 2): (8, 16, True),
+         (16, 4): (8, 16, True), (16, 8): (8, 16, True)}
+EXPECTED_F32_PLANS = {50: _P50, 100: _P100}
+
+
+@pytest.mark.parametrize("N", [50, 100])
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("dims", ALL_DIMS)
+def test_launch_plans_long_horizons_vs_oracle(dims, dt, N):
+    """kernel = GPI (planner's choice) and AUTO on a ragged batch: cold solve + one warm-started solve, every scalar vs the
+    oracle.  fp32: the plan the bench tables quote is asserted through stats()."""
+    nx, nu = dims
+    spec = wl.random_lti(nx, nu, N, seed=7 * nx + nu)
+    prob = setup_problem(spec, dt)
+    st = abi.Settings.from_buffer_copy(spec.settings)
+    st.max_iter = 12
+    B = 37
+    inst = wl.random_instances(B, nx, N, seed=N + nx, dtype=dt)
+    inst["x0"] = (3.0 * inst["x0"]).astype(dt)
+    want = tuple(H.BOX_STATE)
+    o1 = _port(prob, st, inst["x0"], inst["Xref"], None, None, True, want)
+    x0b = (inst["x0"] * dt(0.9)).astype(dt)
+    o2 = _port(prob, st, x0b, inst["Xref"], None, {n: o1[n].copy() for n in H.BOX_STATE}, False, want)
+    for kernel in ("gpi", "auto"):
+        solver = _mk_solver(prob, st, kernel)
+        g1 = solver.solve(inst["x0"], inst["Xref"], None, cold_start=True, want_state=want)
+        stt = solver.stats()
+        for key in H.OUT_KEYS + H.BOX_STATE:
+            assert H.bits_equal(g1[key], o1[key]), (dims, N, kernel, key)
+        g2 = solver.solve(x0b, inst["Xref"], None, state={n: g1[n].copy() for n in H.BOX_STATE}, cold_start=False, want_state=want)
+        for key in H.OUT_KEYS + H.BOX_STATE:
+            assert H.bits_equal(g2[key], o2[key]), (dims, N, kernel, "warm", key)
+        if kernel == "gpi":
+            assert stt["kernel_family"] in (abi.KERNEL_GPI, abi.KERNEL_GPS)
+            exp = EXPECTED_F32_PLANS[N].get(dims)
+            if dt == np.float32 and exp is not None:
+                assert stt["kernel_family"] == abi.KERNEL_GPI
+                got = (stt["lanes_per_instance"], stt["instances_per_cta"], stt["tmem_cols_per_cta"] > 0)
+                assert got == exp, (dims, N, got, exp)
+
+
+def test_full_size_rocket_sample_vs_oracle():
+    """BASELINE config 4 at full size (16384 rocket-landing instances, N = 100, fp64, cones, per-instance references as in
+    bench.py) on the path AUTO picks (streamed lane groups): a strided 256-instance sample against the oracle, all scalars."""
+    import torch
+
+    spec = wl.rocket(N=100)
+    dt = np.float64
+    prob = setup_problem(spec, dt)
+    st = spec.settings
+    B = 16384
+    inst = wl.rocket_instances(B, N=100, seed=0, dtype=dt, per_instance_refs=True)
+    solver = _mk_solver(prob, st, "auto")
+    batch, out = solver.make_device_batch(inst["x0"], inst["Xref"], inst["Uref"], cold_start=True)
+    solver.solve_device(batch)
+    torch.cuda.synchronize()
+    stt = solver.stats()
+    assert stt["kernel_family"] == abi.KERNEL_GPS and stt["kernel_launches"] == 1
+    g = {k: v.cpu().numpy() for k, v in out.items() if v is not None}
+    idx = np.unique(np.concatenate([np.arange(0, B, B // 248), np.arange(B - 8, B)]))
+    o = _port(prob, st, inst["x0"][idx], inst["Xref"][idx], inst["Uref"][idx], None, True, ())
+    for key in H.OUT_KEYS:
+        assert H.bits_equal(g[key][idx], o[key]), key
+    assert int(g["iter"].sum()) == 100 * B  # never converges in the reference either: fixed work
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_device_precompute_vs_reference_tiny_setup(dt):
+    """SURVEY §8f-2 against the REFERENCE: the device precompute's blobs vs tiny_setup of the compiled reference
+    (oracle.ref_setup -> tiny_api.cpp:21-147,307-381), per model.  fp64: <= 1e-9 of the matrix's largest entry; fp32:
+    <= 1e-5 where the Riccati fixed point converges in float, <= 1e-4 where it never does (quadrotor: 1000 sweeps of a
+    rounding-level limit cycle — Eigen's inverse and the product's Gauss-Jordan then differ in the last bits each sweep)."""
+    import torch
+    from tinympc_b200.solver import unpack_model
+
+    if not oracle.ref_available(dt):
+        pytest.skip("compiled reference not present")
+    for nx, nu, specs in ((12, 4, [wl.quadrotor(N=10), wl.quadrotor(N=10, hz=50)] + [wl.random_lti(12, 4, 10, seed=i) for i in range(6)]),
+                          (6, 3, [wl.rocket(N=10)] + [wl.random_lti(6, 3, 10, seed=i) for i in range(5)]),
+                          (16, 8, [wl.random_lti(16, 8, 10, seed=i) for i in range(6)])):
+        prob = setup_problem(specs[0], dt)
+        solver = _mk_solver(prob, specs[0].settings, "auto")
+        args = (np.stack([s.A for s in specs]), np.stack([np.asarray(s.B).reshape(nx, nu) for s in specs]), np.stack([s.f for s in specs]),
+                np.stack([s.Qdiag for s in specs]), np.stack([s.Rdiag for s in specs]), np.array([s.rho for s in specs]))
+        dev, sweeps = solver.setup_models_device(*args, want_sweeps=True)
+        torch.cuda.synchronize()
+        dev, sweeps = dev.cpu().numpy(), sweeps.cpu().numpy()
+        for i, sp in enumerate(specs):
+            ref = H.problem_from_spec(sp, dt, oracle.ref_setup)
+            m = unpack_model(dev[i], nx, nu)
+            tol = 1e-9 if dt == np.float64 else (1e-5 if sweeps[i] < 1000 else 1e-4)
+            for f in ("Q", "R", "Kinf", "Pinf", "Quu_inv", "AmBKt", "APf", "BPf"):
+                a, b = np.asarray(m[f], np.float64).reshape(-1), np.asarray(getattr(ref, f), np.float64).reshape(-1, order="F")
+                scale = max(float(np.abs(b).max()), 1e-30)
+                assert float(np.abs(a - b).max()) <= tol * scale, (sp.name, i, f, float(np.abs(a - b).max()) / scale, int(sweeps[i]))
+
+
+def test_closed_loop_without_previous_slacks_equals_reference_with_v_z_zeroed():
+    """DeviceMPCLoop(exact_first_residual=False) drops work->v / work->z between steps.  Parity statement: that mode is the
+    reference's loop with work->v and work->z zeroed before every tiny_solve — bit for bit (v, z only enter the dual
+    residual of a solve's first iteration, admm.cpp:315,317)."""
+    from tinympc_b200.closed_loop import DeviceMPCLoop
+
+    spec = wl.quadrotor(N=10)
+    dt = np.float32
+    prob = setup_problem(spec, dt)
+    st = spec.settings
+    B, steps = 200, 5
+    inst = wl.tracking_instances(B, N=10, seed=5, dtype=dt)
+    loop = DeviceMPCLoop(_mk_solver(prob, st, "auto"), inst["x0"], reset_duals=True, exact_first_residual=False)
+    x0, state = inst["x0"].copy(), None
+    for k in range(steps):
+        Xref = np.ascontiguousarray(np.roll(inst["Xref"], -k, axis=1))
+        out = loop.step(Xref)
+        if state is not None:
+            for n in ("g", "y", "v", "z"):
+                state[n] = np.zeros_like(state[n])
+        o = _port(prob, st, x0, Xref, None, state, state is None, tuple(H.BOX_STATE))
+        for key in H.OUT_KEYS + list(loop.fields):
+            assert H.bits_equal(out[key].cpu().numpy(), o[key]), (k, key)
+        state = {n: o[n] for n in H.BOX_STATE}
+        x0 = loop.x0.cpu().numpy().copy()  # the plant update itself is covered by test_device_resident_closed_loop_matches_oracle

@@ -127,11 +127,34 @@ __device__ __forceinline__ void cp_wait(int pending) {  // warp-uniform argument
     else if (pending == 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
     else asm volatile("cp.async.wait_group 3;" ::: "memory");
 }
+template <int PENDING>
+__device__ __forceinline__ void cp_wait_c() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory");
+}
+// predicated forms (pr != 0: do it): one PTX predicate instead of a branch around the copy.  Lanes that own only padding
+// rows skip their copies / stores this way; a branch per guarded group cost 9 % of the kernel's instructions (BSSY / BRA /
+// BSYNC, ncu source view of the rocket-landing solve) and every reconvergence point is a scheduling barrier for ptxas.
+template <int BYTES>
+__device__ __forceinline__ void cp_async_p(unsigned dst, const void *src, unsigned pr) {
+    static_assert(BYTES == 4 || BYTES == 8 || BYTES == 16, "cp.async moves 4, 8 or 16 bytes");
+    if constexpr (BYTES == 16) {
+        asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %2, 0;\n @q cp.async.cg.shared.global [%0], [%1], 16;\n}" ::"r"(dst), "l"(src), "r"(pr) : "memory");
+    } else if constexpr (BYTES == 8) {
+        asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %2, 0;\n @q cp.async.ca.shared.global [%0], [%1], 8;\n}" ::"r"(dst), "l"(src), "r"(pr) : "memory");
+    } else {
+        asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %2, 0;\n @q cp.async.ca.shared.global [%0], [%1], 4;\n}" ::"r"(dst), "l"(src), "r"(pr) : "memory");
+    }
+}
 // a lane's piece of PB bytes in chunks of CB bytes
 template <int PB, int CB>
 __device__ __forceinline__ void cp_piece(unsigned dst, const void *src) {
 #pragma unroll
     for (int c = 0; c < PB / CB; ++c) cp_async<CB>(dst + (unsigned)(c * CB), reinterpret_cast<const char *>(src) + c * CB);
+}
+template <int PB, int CB>
+__device__ __forceinline__ void cp_piece(unsigned dst, const void *src, unsigned pr) {
+#pragma unroll
+    for (int c = 0; c < PB / CB; ++c) cp_async_p<CB>(dst + (unsigned)(c * CB), reinterpret_cast<const char *>(src) + c * CB, pr);
 }
 
 // ---- chunked piece moves between registers and shared / global memory ----
@@ -154,6 +177,24 @@ __device__ __forceinline__ void stg_chunk(float *p, const float (&v)[2]) { *rein
 __device__ __forceinline__ void stg_chunk(float *p, const float (&v)[4]) { *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]); }
 __device__ __forceinline__ void stg_chunk(double *p, const double (&v)[1]) { *p = v[0]; }
 __device__ __forceinline__ void stg_chunk(double *p, const double (&v)[2]) { *reinterpret_cast<double2 *>(p) = make_double2(v[0], v[1]); }
+// predicated stores (see cp_async_p)
+__device__ __forceinline__ void stg_chunk(float *p, const float (&v)[1], unsigned pr) {
+    asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %2, 0;\n @q st.global.f32 [%0], %1;\n}" ::"l"(p), "f"(v[0]), "r"(pr) : "memory");
+}
+__device__ __forceinline__ void stg_chunk(float *p, const float (&v)[2], unsigned pr) {
+    asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %3, 0;\n @q st.global.v2.f32 [%0], {%1,%2};\n}" ::"l"(p), "f"(v[0]), "f"(v[1]), "r"(pr) : "memory");
+}
+__device__ __forceinline__ void stg_chunk(float *p, const float (&v)[4], unsigned pr) {
+    asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %5, 0;\n @q st.global.v4.f32 [%0], {%1,%2,%3,%4};\n}" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+                 "f"(v[3]), "r"(pr)
+                 : "memory");
+}
+__device__ __forceinline__ void stg_chunk(double *p, const double (&v)[1], unsigned pr) {
+    asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %2, 0;\n @q st.global.f64 [%0], %1;\n}" ::"l"(p), "d"(v[0]), "r"(pr) : "memory");
+}
+__device__ __forceinline__ void stg_chunk(double *p, const double (&v)[2], unsigned pr) {
+    asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %3, 0;\n @q st.global.v2.f64 [%0], {%1,%2};\n}" ::"l"(p), "d"(v[0]), "d"(v[1]), "r"(pr) : "memory");
+}
 
 template <typename T, int R, int CB>
 __device__ __forceinline__ void lds_piece(unsigned a, T (&v)[R]) {
@@ -186,6 +227,17 @@ __device__ __forceinline__ void stg_piece(T *p, const T (&v)[R]) {
 #pragma unroll
         for (int e = 0; e < E; ++e) t[e] = v[c * E + e];
         stg_chunk(p + c * E, t);
+    }
+}
+template <typename T, int R, int CB>
+__device__ __forceinline__ void stg_piece(T *p, const T (&v)[R], unsigned pr) {
+    constexpr int E = CB / (int)sizeof(T);
+#pragma unroll
+    for (int c = 0; c < R / E; ++c) {
+        T t[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) t[e] = v[c * E + e];
+        stg_chunk(p + c * E, t, pr);
     }
 }
 
@@ -258,6 +310,7 @@ __global__ void __launch_bounds__(GPS_MAX_WARPS * 32, 1)
         }
     }
     const bool xvl = l * RX < NX, uvl = l * RU < NU;  // does this lane own real rows (else padding rows: zeros)
+    const unsigned pxv = xvl ? 1u : 0u, puv = uvl ? 1u : 0u;  // the same as PTX predicate sources (predicated copies / stores)
     // The staged blob stays in shared memory for the whole kernel.  A sweep only needs half of the matrices (forward:
     // A, Kinf, B; backward: AmBKt, B^T, Kinf^T, Quu_inv), so each sweep pulls this lane's rows of ITS matrices into
     // registers when it starts: about half the register footprint of keeping everything resident, which is what makes
@@ -491,41 +544,46 @@ __global__ void __launch_bounds__(GPS_MAX_WARPS * 32, 1)
         if (k < N) {
             const unsigned bx = aXl + sb, bu = aUl + sb;
 #pragma unroll
+            const unsigned pu_ = (k < N - 1) ? puv : 0u;
             for (int j = 0; j < NI; ++j) {
-                if (xvl) {
-                    cp_piece<RX * ES, CX>(bx + (0 * NI + j) * PXB, cx + REC::vnew + j * JX);
-                    cp_piece<RX * ES, CX>(bx + (1 * NI + j) * PXB, cx + REC::g + j * JX);
-                    cp_piece<RX * ES, ES>(bx + (2 * NI + j) * PXB, xr[j]);
-                    if constexpr ((FAM & 1) != 0)
-                        if (fx[0]) cp_piece<RX * ES, CX>(bx + ((3 + Cfg::fslot(0)) * NI + j) * PXB, cx + REC::gf(0) + j * JX);
-                    if constexpr ((FAM & 2) != 0)
-                        if (fx[1]) cp_piece<RX * ES, CX>(bx + ((3 + Cfg::fslot(1)) * NI + j) * PXB, cx + REC::gf(1) + j * JX);
-                    if constexpr ((FAM & 4) != 0)
-                        if (fx[2]) cp_piece<RX * ES, CX>(bx + ((3 + Cfg::fslot(2)) * NI + j) * PXB, cx + REC::gf(2) + j * JX);
-                }
-                if (uvl && k < N - 1) {
-                    cp_piece<RU * ES, CU>(bu + (0 * NI + j) * PUB, cu + REC::d + j * JU);
-                    cp_piece<RU * ES, CU>(bu + (1 * NI + j) * PUB, cu + REC::znew + j * JU);
-                    cp_piece<RU * ES, CU>(bu + (2 * NI + j) * PUB, cu + REC::y + j * JU);
-                    if (has_uref) cp_piece<RU * ES, ES>(bu + (3 * NI + j) * PUB, ur[j]);
-                    if constexpr ((FAM & 1) != 0)
-                        if (fu[0]) cp_piece<RU * ES, CU>(bu + ((4 + Cfg::fslot(0)) * NI + j) * PUB, cu + REC::yf(0) + j * JU);
-                    if constexpr ((FAM & 2) != 0)
-                        if (fu[1]) cp_piece<RU * ES, CU>(bu + ((4 + Cfg::fslot(1)) * NI + j) * PUB, cu + REC::yf(1) + j * JU);
-                    if constexpr ((FAM & 4) != 0)
-                        if (fu[2]) cp_piece<RU * ES, CU>(bu + ((4 + Cfg::fslot(2)) * NI + j) * PUB, cu + REC::yf(2) + j * JU);
-                }
+                cp_piece<RX * ES, CX>(bx + (0 * NI + j) * PXB, cx + REC::vnew + j * JX, pxv);
+                cp_piece<RX * ES, CX>(bx + (1 * NI + j) * PXB, cx + REC::g + j * JX, pxv);
+                cp_piece<RX * ES, ES>(bx + (2 * NI + j) * PXB, xr[j], pxv);
+                if constexpr ((FAM & 1) != 0)
+                    if (fx[0]) cp_piece<RX * ES, CX>(bx + ((3 + Cfg::fslot(0)) * NI + j) * PXB, cx + REC::gf(0) + j * JX, pxv);
+                if constexpr ((FAM & 2) != 0)
+                    if (fx[1]) cp_piece<RX * ES, CX>(bx + ((3 + Cfg::fslot(1)) * NI + j) * PXB, cx + REC::gf(1) + j * JX, pxv);
+                if constexpr ((FAM & 4) != 0)
+                    if (fx[2]) cp_piece<RX * ES, CX>(bx + ((3 + Cfg::fslot(2)) * NI + j) * PXB, cx + REC::gf(2) + j * JX, pxv);
+                cp_piece<RU * ES, CU>(bu + (0 * NI + j) * PUB, cu + REC::d + j * JU, pu_);
+                cp_piece<RU * ES, CU>(bu + (1 * NI + j) * PUB, cu + REC::znew + j * JU, pu_);
+                cp_piece<RU * ES, CU>(bu + (2 * NI + j) * PUB, cu + REC::y + j * JU, pu_);
+                if (has_uref) cp_piece<RU * ES, ES>(bu + (3 * NI + j) * PUB, ur[j], pu_);
+                if constexpr ((FAM & 1) != 0)
+                    if (fu[0]) cp_piece<RU * ES, CU>(bu + ((4 + Cfg::fslot(0)) * NI + j) * PUB, cu + REC::yf(0) + j * JU, pu_);
+                if constexpr ((FAM & 2) != 0)
+                    if (fu[1]) cp_piece<RU * ES, CU>(bu + ((4 + Cfg::fslot(1)) * NI + j) * PUB, cu + REC::yf(1) + j * JU, pu_);
+                if constexpr ((FAM & 4) != 0)
+                    if (fu[2]) cp_piece<RU * ES, CU>(bu + ((4 + Cfg::fslot(2)) * NI + j) * PUB, cu + REC::yf(2) + j * JU, pu_);
             }
         }
         cp_commit();
     };
-    auto issue_bwd = [&](int k, unsigned sb, const T *cx, const T *cu) {
+    // The backward sweep fetches only q_k, r_k (one state-shaped and one input-shaped piece per instance) and does a third
+    // of the forward sweep's arithmetic per step, so two steps of look-ahead do not cover the L2 / HBM latency there (ncu:
+    // the ring read of r_k alone held 5 % of the stall samples).  It therefore cuts the same ring memory into smaller
+    // stages — one piece slot of the forward layout per stage, BS of them — and runs DB steps ahead.  Piece slots keep
+    // their per-lane slices, so the slices of padding lanes still never receive data.
+    constexpr int BS = S * Cfg::XP, DB = (BS - 1 < 6) ? BS - 1 : 6;
+    auto bwd_off_x = [&](int t) { return (unsigned)(t / Cfg::XP) * STAGE + (unsigned)(t % Cfg::XP) * (NI * PXB); };
+    auto bwd_off_u = [&](int t) { return (unsigned)(t / Cfg::XP) * STAGE + (unsigned)(t % Cfg::XP) * (NI * PUB); };
+    auto issue_bwd = [&](int k, int t, const T *cx, const T *cu) {
         if (k >= 0) {
-            const unsigned bx = aXl + sb, bu = aUl + sb;
+            const unsigned bx = aXl + bwd_off_x(t), bu = aUl + bwd_off_u(t);
 #pragma unroll
             for (int j = 0; j < NI; ++j) {
-                if (xvl) cp_piece<RX * ES, CX>(bx + j * PXB, cx + REC::q + j * JX);
-                if (uvl && k < N - 1) cp_piece<RU * ES, CU>(bu + j * PUB, cu + REC::r + j * JU);
+                cp_piece<RX * ES, CX>(bx + j * PXB, cx + REC::q + j * JX, pxv);
+                cp_piece<RU * ES, CU>(bu + j * PUB, cu + REC::r + j * JU, (k < N - 1) ? puv : 0u);
             }
         }
         cp_commit();
@@ -555,10 +613,8 @@ __global__ void __launch_bounds__(GPS_MAX_WARPS * 32, 1)
                     gfn[a] = (gf[j][a] + xo[j][a]) - sf[j][a];
                     q[j][a] = nmac<FAST>(q[j][a], rho, sf[j][a] - gfn[a]);
                 }
-                if (xvl) {
-                    stg_piece<T, RX, CX>(cx + REC::gf(F) + j * JX, gfn);
-                    if (keep_f[F]) stg_piece<T, RX, CX>(wsb + (int64_t)k * recB + REC::vf(F) + (j * IPW + grp) * NX + l * RX, sf[j]);
-                }
+                stg_piece<T, RX, CX>(cx + REC::gf(F) + j * JX, gfn, pxv);
+                if (keep_f[F]) stg_piece<T, RX, CX>(wsb + (int64_t)k * recB + REC::vf(F) + (j * IPW + grp) * NX + l * RX, sf[j], pxv);
             }
         }
         if (fu[F] && HASU) {
@@ -579,10 +635,8 @@ __global__ void __launch_bounds__(GPS_MAX_WARPS * 32, 1)
                     yfn[b] = (yf[j][b] + u[j][b]) - sf[j][b];
                     r[j][b] = nmac<FAST>(r[j][b], rho, sf[j][b] - yfn[b]);
                 }
-                if (uvl) {
-                    stg_piece<T, RU, CU>(cu + REC::yf(F) + j * JU, yfn);
-                    if (keep_f[F]) stg_piece<T, RU, CU>(wsb + (int64_t)k * recB + REC::zf(F) + (j * IPW + grp) * NU + l * RU, sf[j]);
-                }
+                stg_piece<T, RU, CU>(cu + REC::yf(F) + j * JU, yfn, puv);
+                if (keep_f[F]) stg_piece<T, RU, CU>(wsb + (int64_t)k * recB + REC::zf(F) + (j * IPW + grp) * NU + l * RU, sf[j], puv);
             }
         }
     };
@@ -667,11 +721,9 @@ __global__ void __launch_bounds__(GPS_MAX_WARPS * 32, 1)
                     const T base = HASU ? -(xrf[a] * vQd[a]) : pt[a];
                     q[j][a] = nmac<FAST>(base, rho, v - gn[a]);
                 }
-                if (xvl) {
-                    stg_piece<T, RX, CX>(cx + REC::vnew + j * JX, vn);
-                    stg_piece<T, RX, CX>(cx + REC::g + j * JX, gn);
-                    if (keep_v) stg_piece<T, RX, CX>(wsb + (int64_t)k * recB + REC::vprev + (j * IPW + grp) * NX + l * RX, vo);
-                }
+                stg_piece<T, RX, CX>(cx + REC::vnew + j * JX, vn, pxv);
+                stg_piece<T, RX, CX>(cx + REC::g + j * JX, gn, pxv);
+                if (keep_v) stg_piece<T, RX, CX>(wsb + (int64_t)k * recB + REC::vprev + (j * IPW + grp) * NX + l * RX, vo, pxv);
 #pragma unroll
                 for (int b = 0; b < RU; ++b) r[j][b] = T(0);
                 if (HASU) {
@@ -689,11 +741,9 @@ __global__ void __launch_bounds__(GPS_MAX_WARPS * 32, 1)
                         const T urb = has_uref ? urf[b] : T(0);
                         r[j][b] = nmac<FAST>(-(urb * vRd[b]), rho, z - yn[b]);
                     }
-                    if (uvl) {
-                        stg_piece<T, RU, CU>(cu + REC::znew + j * JU, zn);
-                        stg_piece<T, RU, CU>(cu + REC::y + j * JU, yn);
-                        if (keep_v) stg_piece<T, RU, CU>(wsb + (int64_t)k * recB + REC::zprev + (j * IPW + grp) * NU + l * RU, zo);
-                    }
+                    stg_piece<T, RU, CU>(cu + REC::znew + j * JU, zn, puv);
+                    stg_piece<T, RU, CU>(cu + REC::y + j * JU, yn, puv);
+                    if (keep_v) stg_piece<T, RU, CU>(wsb + (int64_t)k * recB + REC::zprev + (j * IPW + grp) * NU + l * RU, zo, puv);
                 }
             }
             // ---- cones (family 0): state and input side together ----
@@ -720,10 +770,8 @@ __global__ void __launch_bounds__(GPS_MAX_WARPS * 32, 1)
                                 gfn[a] = (gf[j][a] + xo[j][a]) - sx[j][a];
                                 q[j][a] = nmac<FAST>(q[j][a], rho, sx[j][a] - gfn[a]);
                             }
-                            if (xvl) {
-                                stg_piece<T, RX, CX>(cx + REC::gf(0) + j * JX, gfn);
-                                if (keep_f[0]) stg_piece<T, RX, CX>(wsb + (int64_t)k * recB + REC::vf(0) + (j * IPW + grp) * NX + l * RX, sx[j]);
-                            }
+                            stg_piece<T, RX, CX>(cx + REC::gf(0) + j * JX, gfn, pxv);
+                            if (keep_f[0]) stg_piece<T, RX, CX>(wsb + (int64_t)k * recB + REC::vf(0) + (j * IPW + grp) * NX + l * RX, sx[j], pxv);
                         }
                         if (fu[0] && HASU) {
                             T yfn[RU];
@@ -732,10 +780,8 @@ __global__ void __launch_bounds__(GPS_MAX_WARPS * 32, 1)
                                 yfn[b] = (yf[j][b] + u[j][b]) - su[j][b];
                                 r[j][b] = nmac<FAST>(r[j][b], rho, su[j][b] - yfn[b]);
                             }
-                            if (uvl) {
-                                stg_piece<T, RU, CU>(cu + REC::yf(0) + j * JU, yfn);
-                                if (keep_f[0]) stg_piece<T, RU, CU>(wsb + (int64_t)k * recB + REC::zf(0) + (j * IPW + grp) * NU + l * RU, su[j]);
-                            }
+                            stg_piece<T, RU, CU>(cu + REC::yf(0) + j * JU, yfn, puv);
+                            if (keep_f[0]) stg_piece<T, RU, CU>(wsb + (int64_t)k * recB + REC::zf(0) + (j * IPW + grp) * NU + l * RU, su[j], puv);
                         }
                     }
                 }
@@ -745,8 +791,8 @@ __global__ void __launch_bounds__(GPS_MAX_WARPS * 32, 1)
             if constexpr ((FAM & 4) != 0) planes_family(IdxTag<2>{}, k, HASU, bx, bu, cx, cu, xo, u, q, r);
 #pragma unroll
             for (int j = 0; j < NI; ++j) {
-                if (xvl) stg_piece<T, RX, CX>(cx + REC::q + j * JX, q[j]);
-                if (HASU && uvl) stg_piece<T, RU, CU>(cu + REC::r + j * JU, r[j]);
+                stg_piece<T, RX, CX>(cx + REC::q + j * JX, q[j], pxv);
+                if (HASU) stg_piece<T, RU, CU>(cu + REC::r + j * JU, r[j], puv);
             }
             if (HASU) {  // x_{k+1} = (A x_k + B u_k) + f                                  (admm.cpp:30)
 #pragma unroll
@@ -778,28 +824,29 @@ __global__ void __launch_bounds__(GPS_MAX_WARPS * 32, 1)
         load_bwd_rows(mS1b, mKt, mQuu, vAPf, vBPf);
         T *cx = px0 + (int64_t)(N - 1) * recA, *cu = pu0 + (int64_t)(N - 1) * recA;  // record of the current knot point
 #pragma unroll
-        for (int t = 0; t < D; ++t) issue_bwd(N - 1 - t, (unsigned)t * STAGE, cx - t * recA, cu - t * recA);
-        unsigned sb = 0, sbi = (unsigned)(D % S) * STAGE;
+        for (int t = 0; t < DB; ++t) issue_bwd(N - 1 - t, t, cx - t * recA, cu - t * recA);
+        int tc = 0, ti = DB % BS;  // ring stage of the current step / of the step being fetched
         T po[NI][RX], Pf[NI][NX];
         {   // terminal cost p_{N-1}
-            issue_bwd(N - 1 - D, sbi, cx - D * recA, cu - D * recA);
-            cp_wait(D);
+            issue_bwd(N - 1 - DB, ti, cx - DB * recA, cu - DB * recA);
+            cp_wait_c<DB>();
 #pragma unroll
-            for (int j = 0; j < NI; ++j) lds_piece<T, RX, SX>(aXl + sb + j * PXB, po[j]);
+            for (int j = 0; j < NI; ++j) lds_piece<T, RX, SX>(aXl + bwd_off_x(tc) + j * PXB, po[j]);
             gather_x(po, Pf);
             cx -= recA;
             cu -= recA;
-            sb = (sb + STAGE == S * STAGE) ? 0u : sb + STAGE;
-            sbi = (sbi + STAGE == S * STAGE) ? 0u : sbi + STAGE;
+            tc = (tc + 1 == BS) ? 0 : tc + 1;
+            ti = (ti + 1 == BS) ? 0 : ti + 1;
         }
         for (int k = N - 2; k >= 0; --k) {
-            issue_bwd(k - D, sbi, cx - D * recA, cu - D * recA);
-            cp_wait(D);
+            issue_bwd(k - DB, ti, cx - DB * recA, cu - DB * recA);
+            cp_wait_c<DB>();
             T q[NI][RX], r[NI][RU], Rf[NI][NU];
+            const unsigned ox = aXl + bwd_off_x(tc), ou = aUl + bwd_off_u(tc);
 #pragma unroll
             for (int j = 0; j < NI; ++j) {
-                lds_piece<T, RX, SX>(aXl + sb + j * PXB, q[j]);
-                lds_piece<T, RU, SU>(aUl + sb + j * PUB, r[j]);
+                lds_piece<T, RX, SX>(ox + j * PXB, q[j]);
+                lds_piece<T, RU, SU>(ou + j * PUB, r[j]);
             }
             gather_u(r, Rf);
             // d_k = Quu_inv ((B^T p_{k+1} + r_k) + BPf)
@@ -824,12 +871,12 @@ __global__ void __launch_bounds__(GPS_MAX_WARPS * 32, 1)
             for (int j = 0; j < NI; ++j) {
                 T dq[RU];
                 dots<FAST>(mQuu, Sf[j], dq);
-                if (uvl) stg_piece<T, RU, CU>(cu + REC::d + j * JU, dq);
+                stg_piece<T, RU, CU>(cu + REC::d + j * JU, dq, puv);
             }
             cx -= recA;
             cu -= recA;
-            sb = (sb + STAGE == S * STAGE) ? 0u : sb + STAGE;
-            sbi = (sbi + STAGE == S * STAGE) ? 0u : sbi + STAGE;
+            tc = (tc + 1 == BS) ? 0 : tc + 1;
+            ti = (ti + 1 == BS) ? 0 : ti + 1;
         }
     };
 
@@ -1194,6 +1241,10 @@ int launch_gps(LaunchDesc *d, const KParams<T, NX, NU> &P0) {
         int ni = gps_env_int("TINYMPC_GPS_NI", NIP);
         if (ni != 1 && ni != 2) ni = NIP;
         if (ni > NIP) ni = NIP;
+        (void)ni;
+// only the planner's instances-per-group variant is compiled; -DTM_GPS_TUNE also builds the one-instance variant of the
+// shapes that default to two (TINYMPC_GPS_NI=1 then selects it: developer sweeps)
+#ifdef TM_GPS_TUNE
 #define TM_GPS_CASE(FF)                                                                   \
     if (fam == FF) {                                                                      \
         if constexpr (NIP == 2) {                                                         \
@@ -1201,6 +1252,10 @@ int launch_gps(LaunchDesc *d, const KParams<T, NX, NU> &P0) {
         }                                                                                 \
         return launch_gps_cfg<T, NX, NU, L, 1, FF, FAST>(d, P0);                          \
     }
+#else
+#define TM_GPS_CASE(FF) \
+    if (fam == FF) return launch_gps_cfg<T, NX, NU, L, NIP, FF, FAST>(d, P0);
+#endif
         TM_GPS_CASE(0)
         TM_GPS_CASE(1)
         TM_GPS_CASE(6)

@@ -5,7 +5,9 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -30,6 +32,27 @@ struct Impl {
 std::map<TinySolver *, Impl> &table() {
     static std::map<TinySolver *, Impl> t;
     return t;
+}
+// The reference is safe with one TinySolver per thread (SURVEY §8b "Threading"): the handle table is the only state
+// shared between solvers, so look-ups / inserts / erases take this lock.  std::map nodes are stable, so the Impl& a
+// thread obtained stays valid while other threads insert.
+std::mutex &table_mutex() {
+    static std::mutex m;
+    return m;
+}
+Impl &impl_of(TinySolver *s) {
+    std::lock_guard<std::mutex> lk(table_mutex());
+    return table()[s];
+}
+
+#include "sensitivity_tables.inc"
+
+[[noreturn]] void fused_stage(const char *name) {
+    std::fprintf(stderr,
+                 "tinympc_b200 shim: %s() is not available as a separate call - the ADMM stages (admm.hpp:9-34) are fused into one "
+                 "batched GPU kernel; call tiny_solve()/solve() (one whole solve) or the C ABI (tinympc_b200_solve).\n",
+                 name);
+    std::abort();
 }
 
 uint64_t fnv(uint64_t h, const void *p, size_t n) {
@@ -350,9 +373,10 @@ int tiny_set_u_ref(TinySolver *s, tinyMatrix u_ref) {
     return 0;
 }
 
-int tiny_solve(TinySolver *s) {
+// admm.hpp:9 — the ADMM driver itself (admm.cpp:331-455); tiny_solve is the reference's trampoline onto it
+int solve(TinySolver *s) {
     TinyWorkspace *w = s->work;
-    Impl &im = table()[s];
+    Impl &im = impl_of(s);
     if (ensure_handle(s, im)) return 1;
     push_settings(s, im);
     const long nx = w->nx, nu = w->nu, N = w->N;
@@ -391,12 +415,51 @@ int tiny_solve(TinySolver *s) {
     return solved ? 0 : 1;
 }
 
+int tiny_solve(TinySolver *s) { return solve(s); }  // tiny_api.cpp:384-386
+
+// admm.hpp:12-17 — the six stage functions exist as symbols so that programs referencing them link; on this backend the
+// stages only exist fused inside the solve kernel, so calling one is a loud error, never a silent CPU computation.
+void update_linear_cost(TinySolver *) { fused_stage("update_linear_cost"); }
+void backward_pass_grad(TinySolver *) { fused_stage("backward_pass_grad"); }
+void forward_pass(TinySolver *) { fused_stage("forward_pass"); }
+void update_slack(TinySolver *) { fused_stage("update_slack"); }
+void update_dual(TinySolver *) { fused_stage("update_dual"); }
+bool termination_condition(TinySolver *) { fused_stage("termination_condition"); }
+
+// tiny_api.hpp:54 / tiny_api.cpp:479-540: fills the four sensitivity matrices of the cache with the reference's hard-coded
+// (quadrotor-sized: 4x12, 12x12, 4x4, 12x12) tables, whatever the solver's dimensions - as the reference does.  Adaptive rho
+// itself stays out of scope (settings->adaptive_rho must remain 0); this keeps programs that call the initialiser working.
+void tiny_initialize_sensitivity_matrices(TinySolver *s) {
+    if (!s || !s->cache) return;
+    s->cache->dKinf_drho = Map<const Matrix<double, 4, 12>>(k_dKinf_drho);
+    s->cache->dPinf_drho = Map<const Matrix<double, 12, 12>>(k_dPinf_drho);
+    s->cache->dC1_drho = Map<const Matrix<double, 4, 4>>(k_dC1_drho);
+    s->cache->dC2_drho = Map<const Matrix<double, 12, 12>>(k_dC2_drho);
+}
+
+// plain-C view of the above for bindings / tests: copies the four matrices (column-major, 48 + 144 + 16 + 144 doubles)
+int tinympc_shim_sensitivity_tables(double *dKinf, double *dPinf, double *dC1, double *dC2) {
+    TinySolver s;
+    TinyCache c;
+    s.cache = &c;
+    s.work = nullptr; s.settings = nullptr; s.solution = nullptr;
+    tiny_initialize_sensitivity_matrices(&s);
+    std::memcpy(dKinf, c.dKinf_drho.data(), sizeof(double) * 48);
+    std::memcpy(dPinf, c.dPinf_drho.data(), sizeof(double) * 144);
+    std::memcpy(dC1, c.dC1_drho.data(), sizeof(double) * 16);
+    std::memcpy(dC2, c.dC2_drho.data(), sizeof(double) * 144);
+    return 0;
+}
+
 int tiny_destroy(TinySolver *s) {
     if (!s) return 0;
-    auto it = table().find(s);
-    if (it != table().end()) {
-        if (it->second.h) tinympc_b200_destroy(it->second.h);
-        table().erase(it);
+    {
+        std::lock_guard<std::mutex> lk(table_mutex());
+        auto it = table().find(s);
+        if (it != table().end()) {
+            if (it->second.h) tinympc_b200_destroy(it->second.h);
+            table().erase(it);
+        }
     }
     delete s->solution; delete s->cache; delete s->settings; delete s->work; delete s;
     return 0;
@@ -404,7 +467,7 @@ int tiny_destroy(TinySolver *s) {
 
 int tiny_solve_batch(TinySolver *s, const tinyMatrix &x0, const tinyMatrix &Xref, tinyMatrix &u0, VectorXi &iter, VectorXi &solved) {
     TinyWorkspace *w = s->work;
-    Impl &im = table()[s];
+    Impl &im = impl_of(s);
     if (ensure_handle(s, im)) return 1;
     push_settings(s, im);
     const long nx = w->nx, nu = w->nu, N = w->N, B = x0.cols();

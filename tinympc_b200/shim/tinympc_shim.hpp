@@ -43,7 +43,7 @@ typedef struct {
     tinyMatrix Kinf, Pinf, Quu_inv, AmBKt;
     tinyVector APf, BPf;
     tinyMatrix C1, C2;                                     // = Quu_inv, AmBKt (adaptive rho leftovers)
-    tinyMatrix dKinf_drho, dPinf_drho, dC1_drho, dC2_drho;  // never filled (adaptive rho is out of scope)
+    tinyMatrix dKinf_drho, dPinf_drho, dC1_drho, dC2_drho;  // filled by tiny_initialize_sensitivity_matrices only
 } TinyCache;
 
 typedef struct {
@@ -112,7 +112,20 @@ int tiny_set_x0(TinySolver *solver, tinyVector x0);
 int tiny_set_x_ref(TinySolver *solver, tinyMatrix x_ref);
 int tiny_set_u_ref(TinySolver *solver, tinyMatrix u_ref);
 
+void tiny_initialize_sensitivity_matrices(TinySolver *solver);  // tiny_api.hpp:54 (table data, see tinympc_shim.cpp)
+
+// ---- admm.hpp:9-34 ----
+int solve(TinySolver *solver);  // one whole ADMM solve on the GPU (tiny_solve forwards here, as in the reference)
+// The stage functions are fused into the solve kernel; the symbols exist for link compatibility and abort with a message.
+void update_linear_cost(TinySolver *solver);
+void backward_pass_grad(TinySolver *solver);
+void forward_pass(TinySolver *solver);
+void update_slack(TinySolver *solver);
+void update_dual(TinySolver *solver);
+bool termination_condition(TinySolver *solver);
+
 // ---- additions (not in the reference) ----
+int tinympc_shim_sensitivity_tables(double *dKinf, double *dPinf, double *dC1, double *dC2);
 int tiny_destroy(TinySolver *solver);  // the reference has no destroy function (leaks by design)
 // Same problem, B instances: x0 is nx x B, Xref is (nx*N) x B (one column-major trajectory per column);
 // cold start; outputs: u0 (nu x B) = first rollout input of every instance, iter/solved (B).

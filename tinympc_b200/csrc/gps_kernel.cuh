@@ -89,8 +89,33 @@ struct GpsRec {
     __host__ __device__ static constexpr int zf(int f) { return zf0 + fslot(f) * FUE; }
 };
 
-constexpr int GPS_DIST = 2;              // prefetch distance of the cp.async ring (sweep steps)
-constexpr int GPS_STAGES = GPS_DIST + 1;
+constexpr int GPS_STAGES = 4;              // forward-sweep ring stages
+constexpr int GPS_DIST = GPS_STAGES - 1;   // prefetch distance (sweep steps)
+
+// Ring geometry.  A sweep step of a warp needs ONE contiguous block of its record: the forward sweep everything in front of
+// q (d | vnew | g | family duals | znew | y | family duals), the backward sweep q | r.  The block is brought into shared
+// memory as an image of the record by a single TMA bulk copy (cp.async.bulk, issued by one lane, completion on an mbarrier):
+// no per-lane copy instructions and none of their traffic on the LSU / shared-memory data pipe (the per-lane cp.async
+// version spent 41 % of the kernel's shared-memory wavefronts on them, ncu).  The reference columns of a step are not part
+// of the record: every lane loads its own rows straight into registers (ld.global.nc) at the top of the step, behind an L2
+// prefetch issued D steps earlier (staging them per lane through shared memory cost another 17 % of the wavefronts).
+template <int NX, int NU, int L, int ES, int NI, int FAM>
+struct GpsRing {
+    using Cfg = GpsCfg<NX, NU, L, ES, NI, FAM>;
+    using REC = GpsRec<NX, NU, Cfg::SPW, ES, FAM>;
+    static constexpr int IMGF = REC::q * ES;                   // forward image (bytes, a multiple of 16)
+    static constexpr int IMGB = (REC::recA - REC::q) * ES;     // backward image: q | r
+    static constexpr int STAGE = IMGF;
+    static constexpr int S = GPS_STAGES, D = GPS_DIST;
+    static constexpr int RING = S * STAGE;
+    static constexpr int BS = (RING / IMGB) < 8 ? (RING / IMGB) : 8;  // backward stages cut from the same memory
+    static constexpr int DB = BS - 1 < 6 ? BS - 1 : 6;                // backward prefetch distance
+    static constexpr int NBAR = S > BS ? S : BS;
+    static constexpr size_t WARP_BYTES = (size_t)(Cfg::GBX + Cfg::GBU) * ES + (size_t)Cfg::PARK_BYTES + (size_t)RING + (size_t)((NBAR * 8 + 15) / 16 * 16);
+    static constexpr size_t ZERO_BYTES = (size_t)IMGF;  // per CTA: what padding lanes read instead of a record image
+    static_assert(IMGF % 16 == 0 && IMGB % 16 == 0 && STAGE % 16 == 0, "bulk copies move multiples of 16 bytes");
+    static_assert(BS >= 2, "ring too small for the backward sweep");
+};
 
 // smallest lane-group width whose matrix rows fit in registers (0 = none)
 template <typename T, int NX, int NU>
@@ -106,7 +131,8 @@ constexpr int gps_pick_NI() {
     return GpsCfg<NX, NU, L, (int)sizeof(T), 1, 0>::SWEEP_REGS <= 72 ? 2 : 1;
 }
 
-constexpr int GPS_MAX_WARPS = 8;
+// warps per CTA: one instance per lane group leaves room for twice the warps of the two-instance variant (registers)
+__host__ __device__ constexpr int gps_max_warps(int NI) { return NI == 1 ? 14 : 8; }
 
 // ---- cp.async (per-thread asynchronous global -> shared copies) ----
 template <int BYTES>
@@ -145,6 +171,41 @@ __device__ __forceinline__ void cp_async_p(unsigned dst, const void *src, unsign
         asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %2, 0;\n @q cp.async.ca.shared.global [%0], [%1], 4;\n}" ::"r"(dst), "l"(src), "r"(pr) : "memory");
     }
 }
+// predicated read-only global loads of a lane's rows into registers (pr == 0: the registers keep their zeros) and L2 prefetch
+__device__ __forceinline__ void ldg_chunk(const float *p, float (&v)[1], unsigned pr) {
+    asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %2, 0;\n @q ld.global.nc.f32 %0, [%1];\n}" : "+f"(v[0]) : "l"(p), "r"(pr));
+}
+__device__ __forceinline__ void ldg_chunk(const float *p, float (&v)[2], unsigned pr) {
+    asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %3, 0;\n @q ld.global.nc.v2.f32 {%0,%1}, [%2];\n}" : "+f"(v[0]), "+f"(v[1]) : "l"(p), "r"(pr));
+}
+__device__ __forceinline__ void ldg_chunk(const float *p, float (&v)[4], unsigned pr) {
+    asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %5, 0;\n @q ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];\n}"
+                 : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3])
+                 : "l"(p), "r"(pr));
+}
+__device__ __forceinline__ void ldg_chunk(const double *p, double (&v)[1], unsigned pr) {
+    asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %2, 0;\n @q ld.global.nc.f64 %0, [%1];\n}" : "+d"(v[0]) : "l"(p), "r"(pr));
+}
+__device__ __forceinline__ void ldg_chunk(const double *p, double (&v)[2], unsigned pr) {
+    asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %3, 0;\n @q ld.global.nc.v2.f64 {%0,%1}, [%2];\n}" : "+d"(v[0]), "+d"(v[1]) : "l"(p), "r"(pr));
+}
+template <typename T, int R, int CB>
+__device__ __forceinline__ void ldg_piece(const T *p, T (&v)[R], unsigned pr) {
+    constexpr int E = CB / (int)sizeof(T);
+#pragma unroll
+    for (int c = 0; c < R / E; ++c) {
+        T t[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) t[e] = T(0);
+        ldg_chunk(p + c * E, t, pr);
+#pragma unroll
+        for (int e = 0; e < E; ++e) v[c * E + e] = t[e];
+    }
+}
+__device__ __forceinline__ void prefetch_l2(const void *p, unsigned pr) {
+    asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %1, 0;\n @q prefetch.global.L2 [%0];\n}" ::"l"(p), "r"(pr));
+}
+
 // a lane's piece of PB bytes in chunks of CB bytes
 template <int PB, int CB>
 __device__ __forceinline__ void cp_piece(unsigned dst, const void *src) {
@@ -260,16 +321,17 @@ struct IdxTag {
 };
 
 template <typename T, int NX, int NU, int L, int NI, int FAM, bool FAST>
-__global__ void __launch_bounds__(GPS_MAX_WARPS * 32, 1)
+__global__ void __launch_bounds__(gps_max_warps(NI) * 32, 1)
     gps_solve_kernel(const __grid_constant__ KParams<T, NX, NU> P, const T *__restrict__ gmat, unsigned long long *queue) {
     using Cfg = GpsCfg<NX, NU, L, (int)sizeof(T), NI, FAM>;
     using REC = GpsRec<NX, NU, Cfg::SPW, (int)sizeof(T), FAM>;
     constexpr int RX = Cfg::RX, RU = Cfg::RU, IPW = Cfg::IPW, W = Cfg::W, NXP = Cfg::NXP, NUP = Cfg::NUP;
-    constexpr int D = GPS_DIST, S = GPS_STAGES, recA = REC::recA, recB = REC::recB;
+    using RING = GpsRing<NX, NU, L, (int)sizeof(T), NI, FAM>;
+    constexpr int D = RING::D, S = RING::S, recA = REC::recA, recB = REC::recB;
     constexpr int JX = IPW * NX, JU = IPW * NU;  // element distance between the two instances of a group inside a field
     constexpr int CX = Cfg::CX, CU = Cfg::CU, SX = Cfg::SX, SU = Cfg::SU;
     constexpr unsigned ES = (unsigned)sizeof(T);
-    constexpr unsigned PXB = Cfg::PXB, PUB = Cfg::PUB, STAGE = Cfg::STAGE_BYTES, XPB = NI * Cfg::XP * Cfg::PXB;
+    constexpr unsigned PXB = Cfg::PXB, PUB = Cfg::PUB, STAGE = RING::STAGE, IMGF = RING::IMGF, IMGB = RING::IMGB;
     constexpr bool EXT = FAM != 0;
     static_assert(Cfg::ok, "lane mapping not available for this shape");
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -358,17 +420,53 @@ __global__ void __launch_bounds__(GPS_MAX_WARPS * 32, 1)
     };
 
     // ---- shared memory of this warp: gather scratch (state vectors | input vectors) + cp.async ring (S stages) ----
-    constexpr unsigned wbytes = (unsigned)Cfg::WARP_BYTES;
-    const unsigned aGX = aBlob + BLOB_BYTES + (unsigned)warp * wbytes;
+    constexpr unsigned wbytes = (unsigned)RING::WARP_BYTES;
+    const unsigned aZero = aBlob + BLOB_BYTES;  // IMGF bytes of zeros (per CTA)
+    const unsigned aGX = aZero + (unsigned)RING::ZERO_BYTES + (unsigned)warp * wbytes;
     const unsigned aGU = aGX + (unsigned)Cfg::GBX * ES;
     const unsigned aPark = aGU + (unsigned)Cfg::GBU * ES + (unsigned)lane * (NI * 2 * RX) * ES;  // [j][x0 rows | pterm rows]
     const unsigned aRing = aGU + (unsigned)Cfg::GBU * ES + (unsigned)Cfg::PARK_BYTES;
-    const unsigned aXl = aRing + (unsigned)lane * RX * ES;        // + stage offset + (piece*NI + j)*PXB
-    const unsigned aUl = aRing + XPB + (unsigned)lane * RU * ES;  // + stage offset + (piece*NI + j)*PUB
-    // padding lanes never receive data: their ring slices stay zero
-    for (unsigned o = (unsigned)lane * 16u; o < (unsigned)S * STAGE; o += 32u * 16u)
-        asm volatile("st.shared.v4.f32 [%0], {%1,%1,%1,%1};" ::"r"(aRing + o), "f"(0.f) : "memory");
-    __syncwarp();
+    const unsigned aBar = aRing + (unsigned)RING::RING;  // NBAR mbarriers of this warp
+    // this lane's rows inside a state-shaped / input-shaped field of a record image (first instance of the group)
+    const unsigned lxo = (unsigned)(grp * NX + l * RX) * ES, luo = (unsigned)(grp * NU + l * RU) * ES;
+    // the CTA's zero image: what padding lanes read instead of a record image, so that their arithmetic stays finite and
+    // never reaches a residual
+    for (unsigned o = (unsigned)threadIdx.x * 16u; o < (unsigned)RING::ZERO_BYTES; o += (unsigned)blockDim.x * 16u)
+        asm volatile("st.shared.v4.f32 [%0], {%1,%1,%1,%1};" ::"r"(aZero + o), "f"(0.f) : "memory");
+    if (lane == 0) {
+#pragma unroll
+        for (int b = 0; b < RING::NBAR; ++b) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(aBar + 8u * b));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    unsigned phase = 0;  // bit b = parity the next wait on barrier b expects (warp-uniform)
+    // one bulk copy of `bytes` from `src` (global) to `dst` (shared), completion on barrier b; lane 0 issues
+    auto bulk_load = [&](unsigned dst, const T *src, unsigned bytes, int b) {
+        if (lane == 0) {
+            const unsigned mb = aBar + 8u * (unsigned)b;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                         "r"(bytes), "r"(mb)
+                         : "memory");
+        }
+    };
+    auto bulk_wait = [&](int b) {
+        const unsigned mb = aBar + 8u * (unsigned)b, par = (phase >> b) & 1u;
+        unsigned done = 0;
+        while (!done) {
+            asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                         : "=r"(done)
+                         : "r"(mb), "r"(par)
+                         : "memory");
+        }
+        phase ^= 1u << b;
+    };
+    // the records are written with ordinary stores (all lanes) and read back by bulk copies (async proxy): every lane orders
+    // its stores before later async-proxy operations, the warp converges, then lane 0 may issue copies
+    auto sweep_fence = [&]() {
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+        __syncwarp();
+    };
     // gather scratch of instance j of this lane's group (slot j*IPW + grp): own rows / whole vector
     const unsigned gxf0 = aGX + (unsigned)(grp * NXP) * ES, gxo0 = gxf0 + (unsigned)(l * RX) * ES;
     const unsigned guf0 = aGU + (unsigned)(grp * NUP) * ES, guo0 = guf0 + (unsigned)(l * RU) * ES;
@@ -540,53 +638,24 @@ __global__ void __launch_bounds__(GPS_MAX_WARPS * 32, 1)
 
     // ---- ring producers: all copies of one sweep step form one cp.async group.  cx / cu = this lane's rows in the record
     // of knot point k (first instance of the group), xr / ur = its reference columns; sb = byte offset of the stage ----
-    auto issue_fwd = [&](int k, unsigned sb, const T *cx, const T *cu, const T *(&xr)[NI], const T *(&ur)[NI]) {
+    // forward step k into stage si: the record block of knot point k (one bulk copy); this lane's reference columns of
+    // that step are pulled into L2 (per-instance references come from HBM)
+    auto issue_fwd = [&](int k, int si, const T *(&xr)[NI], const T *(&ur)[NI]) {
         if (k < N) {
-            const unsigned bx = aXl + sb, bu = aUl + sb;
+            bulk_load(aRing + (unsigned)si * STAGE, wsw + (int64_t)k * recA, IMGF, si);
+            const unsigned pu_ = (k < N - 1 && has_uref) ? puv : 0u;
 #pragma unroll
-            const unsigned pu_ = (k < N - 1) ? puv : 0u;
             for (int j = 0; j < NI; ++j) {
-                cp_piece<RX * ES, CX>(bx + (0 * NI + j) * PXB, cx + REC::vnew + j * JX, pxv);
-                cp_piece<RX * ES, CX>(bx + (1 * NI + j) * PXB, cx + REC::g + j * JX, pxv);
-                cp_piece<RX * ES, ES>(bx + (2 * NI + j) * PXB, xr[j], pxv);
-                if constexpr ((FAM & 1) != 0)
-                    if (fx[0]) cp_piece<RX * ES, CX>(bx + ((3 + Cfg::fslot(0)) * NI + j) * PXB, cx + REC::gf(0) + j * JX, pxv);
-                if constexpr ((FAM & 2) != 0)
-                    if (fx[1]) cp_piece<RX * ES, CX>(bx + ((3 + Cfg::fslot(1)) * NI + j) * PXB, cx + REC::gf(1) + j * JX, pxv);
-                if constexpr ((FAM & 4) != 0)
-                    if (fx[2]) cp_piece<RX * ES, CX>(bx + ((3 + Cfg::fslot(2)) * NI + j) * PXB, cx + REC::gf(2) + j * JX, pxv);
-                cp_piece<RU * ES, CU>(bu + (0 * NI + j) * PUB, cu + REC::d + j * JU, pu_);
-                cp_piece<RU * ES, CU>(bu + (1 * NI + j) * PUB, cu + REC::znew + j * JU, pu_);
-                cp_piece<RU * ES, CU>(bu + (2 * NI + j) * PUB, cu + REC::y + j * JU, pu_);
-                if (has_uref) cp_piece<RU * ES, ES>(bu + (3 * NI + j) * PUB, ur[j], pu_);
-                if constexpr ((FAM & 1) != 0)
-                    if (fu[0]) cp_piece<RU * ES, CU>(bu + ((4 + Cfg::fslot(0)) * NI + j) * PUB, cu + REC::yf(0) + j * JU, pu_);
-                if constexpr ((FAM & 2) != 0)
-                    if (fu[1]) cp_piece<RU * ES, CU>(bu + ((4 + Cfg::fslot(1)) * NI + j) * PUB, cu + REC::yf(1) + j * JU, pu_);
-                if constexpr ((FAM & 4) != 0)
-                    if (fu[2]) cp_piece<RU * ES, CU>(bu + ((4 + Cfg::fslot(2)) * NI + j) * PUB, cu + REC::yf(2) + j * JU, pu_);
+                prefetch_l2(xr[j], pxv);
+                prefetch_l2(ur[j], pu_);
             }
         }
-        cp_commit();
     };
-    // The backward sweep fetches only q_k, r_k (one state-shaped and one input-shaped piece per instance) and does a third
-    // of the forward sweep's arithmetic per step, so two steps of look-ahead do not cover the L2 / HBM latency there (ncu:
-    // the ring read of r_k alone held 5 % of the stall samples).  It therefore cuts the same ring memory into smaller
-    // stages — one piece slot of the forward layout per stage, BS of them — and runs DB steps ahead.  Piece slots keep
-    // their per-lane slices, so the slices of padding lanes still never receive data.
-    constexpr int BS = S * Cfg::XP, DB = (BS - 1 < 6) ? BS - 1 : 6;
-    auto bwd_off_x = [&](int t) { return (unsigned)(t / Cfg::XP) * STAGE + (unsigned)(t % Cfg::XP) * (NI * PXB); };
-    auto bwd_off_u = [&](int t) { return (unsigned)(t / Cfg::XP) * STAGE + (unsigned)(t % Cfg::XP) * (NI * PUB); };
-    auto issue_bwd = [&](int k, int t, const T *cx, const T *cu) {
-        if (k >= 0) {
-            const unsigned bx = aXl + bwd_off_x(t), bu = aUl + bwd_off_u(t);
-#pragma unroll
-            for (int j = 0; j < NI; ++j) {
-                cp_piece<RX * ES, CX>(bx + j * PXB, cx + REC::q + j * JX, pxv);
-                cp_piece<RU * ES, CU>(bu + j * PUB, cu + REC::r + j * JU, (k < N - 1) ? puv : 0u);
-            }
-        }
-        cp_commit();
+    // The backward sweep fetches only q_k | r_k and does a third of the forward sweep's arithmetic per step, so it cuts the
+    // same ring memory into smaller stages (BS images of IMGB bytes) and runs DB steps ahead.
+    constexpr int BS = RING::BS, DB = RING::DB;
+    auto issue_bwd = [&](int k, int t) {
+        if (k >= 0) bulk_load(aRing + (unsigned)t * IMGB, wsw + (int64_t)k * recA + REC::q, IMGB, t);
     };
 
     // hyperplane family F (1 static, 2 time-varying) of column k, state side then input side: slack = project(x + dual),
@@ -594,12 +663,12 @@ __global__ void __launch_bounds__(GPS_MAX_WARPS * 32, 1)
     auto planes_family = [&](auto ftag, int k, const bool HASU, unsigned bx, unsigned bu, T *cx, T *cu, const T (&xo)[NI][RX],
                              const T (&u)[NI][RU], T (&q)[NI][RX], T (&r)[NI][RU]) {
         constexpr int F = decltype(ftag)::value;
-        constexpr int SL = Cfg::fslot(F);
+        constexpr int FSEL_ = F;
         if (fx[F]) {
             T gf[NI][RX], sf[NI][RX];
 #pragma unroll
             for (int j = 0; j < NI; ++j) {
-                lds_piece<T, RX, SX>(bx + ((3 + SL) * NI + j) * PXB, gf[j]);
+                lds_piece<T, RX, CX>(bx + (unsigned)(REC::gf(FSEL_) + j * JX) * ES, gf[j]);
 #pragma unroll
                 for (int a = 0; a < RX; ++a) sf[j][a] = xo[j][a] + gf[j][a];
             }
@@ -621,7 +690,7 @@ __global__ void __launch_bounds__(GPS_MAX_WARPS * 32, 1)
             T yf[NI][RU], sf[NI][RU];
 #pragma unroll
             for (int j = 0; j < NI; ++j) {
-                lds_piece<T, RU, SU>(bu + ((4 + SL) * NI + j) * PUB, yf[j]);
+                lds_piece<T, RU, CU>(bu + (unsigned)(REC::yf(FSEL_) + j * JU) * ES, yf[j]);
 #pragma unroll
                 for (int b = 0; b < RU; ++b) sf[j][b] = u[j][b] + yf[j][b];
             }
@@ -655,9 +724,10 @@ __global__ void __launch_bounds__(GPS_MAX_WARPS * 32, 1)
             ur[j] = uref_of(j);
         }
         T *cx = px0, *cu = pu0;  // this lane's rows in the record of the CURRENT knot point
+        sweep_fence();
 #pragma unroll
         for (int t = 0; t < D; ++t) {
-            issue_fwd(t, (unsigned)t * STAGE, cx + t * recA, cu + t * recA, xr, ur);
+            issue_fwd(t, t, xr, ur);
 #pragma unroll
             for (int j = 0; j < NI; ++j) {
                 xr[j] += NX;
@@ -665,11 +735,20 @@ __global__ void __launch_bounds__(GPS_MAX_WARPS * 32, 1)
             }
         }
         gather_x(xo, Xf);
-        unsigned sb = 0, sbi = (unsigned)(D % S) * STAGE;  // stage (byte offset) of the current step / of the step being fetched
+        int sc = 0, si = D % S;  // ring stage of the current step / of the step being fetched
         auto column = [&](int k, const bool HASU) {  // always inlined with a literal HASU
-            issue_fwd(k + D, sbi, cx + D * recA, cu + D * recA, xr, ur);
-            cp_wait(D);
-            const unsigned bx = aXl + sb, bu = aUl + sb;
+            issue_fwd(k + D, si, xr, ur);
+            // this step's reference columns (this lane's rows): issued first, used after the first mat-vec
+            T xrfs[NI][RX], urfs[NI][RU];
+#pragma unroll
+            for (int j = 0; j < NI; ++j) {
+                ldg_piece<T, RX, CX>(xr[j] - D * NX, xrfs[j], pxv);
+                ldg_piece<T, RU, CU>(ur[j] - D * NU, urfs[j], (HASU && has_uref) ? puv : 0u);
+            }
+            bulk_wait(sc);
+            const unsigned sb = (unsigned)sc * STAGE;
+            // record image of this step as seen by this lane (padding lanes: the zero image)
+            const unsigned bx = xvl ? aRing + sb + lxo : aZero, bu = uvl ? aRing + sb + luo : aZero;
             T t1[NI][RX + RU], u[NI][RU], Uf[NI][NU];
 #pragma unroll
             for (int j = 0; j < NI; ++j)
@@ -678,7 +757,7 @@ __global__ void __launch_bounds__(GPS_MAX_WARPS * 32, 1)
             if (HASU) {
                 T dk[NI][RU];
 #pragma unroll
-                for (int j = 0; j < NI; ++j) lds_piece<T, RU, SU>(bu + (0 * NI + j) * PUB, dk[j]);
+                for (int j = 0; j < NI; ++j) lds_piece<T, RU, CU>(bu + (unsigned)(REC::d + j * JU) * ES, dk[j]);
 #pragma unroll
                 for (int j = 0; j < NI; ++j) dots<FAST>(mS1f, Xf[j], t1[j]);  // [A x_k ; Kinf x_k]
 #pragma unroll
@@ -706,9 +785,10 @@ __global__ void __launch_bounds__(GPS_MAX_WARPS * 32, 1)
 #pragma unroll
             for (int j = 0; j < NI; ++j) {
                 T vo[RX], g[RX], xrf[RX], vn[RX], gn[RX], pt[RX];
-                lds_piece<T, RX, SX>(bx + (0 * NI + j) * PXB, vo);
-                lds_piece<T, RX, SX>(bx + (1 * NI + j) * PXB, g);
-                lds_piece<T, RX, SX>(bx + (2 * NI + j) * PXB, xrf);
+                lds_piece<T, RX, CX>(bx + (unsigned)(REC::vnew + j * JX) * ES, vo);
+                lds_piece<T, RX, CX>(bx + (unsigned)(REC::g + j * JX) * ES, g);
+#pragma unroll
+                for (int a = 0; a < RX; ++a) xrf[a] = xrfs[j][a];
                 if (!HASU) load_pterm(j, pt);
 #pragma unroll
                 for (int a = 0; a < RX; ++a) {
@@ -728,9 +808,10 @@ __global__ void __launch_bounds__(GPS_MAX_WARPS * 32, 1)
                 for (int b = 0; b < RU; ++b) r[j][b] = T(0);
                 if (HASU) {
                     T zo[RU], y[RU], urf[RU], zn[RU], yn[RU];
-                    lds_piece<T, RU, SU>(bu + (1 * NI + j) * PUB, zo);
-                    lds_piece<T, RU, SU>(bu + (2 * NI + j) * PUB, y);
-                    lds_piece<T, RU, SU>(bu + (3 * NI + j) * PUB, urf);
+                    lds_piece<T, RU, CU>(bu + (unsigned)(REC::znew + j * JU) * ES, zo);
+                    lds_piece<T, RU, CU>(bu + (unsigned)(REC::y + j * JU) * ES, y);
+#pragma unroll
+                    for (int b = 0; b < RU; ++b) urf[b] = urfs[j][b];
 #pragma unroll
                     for (int b = 0; b < RU; ++b) {
                         const T z = clamp_box<FAST>(u[j][b] + y[b], loU[b], hiU[b]);
@@ -749,12 +830,12 @@ __global__ void __launch_bounds__(GPS_MAX_WARPS * 32, 1)
             // ---- cones (family 0): state and input side together ----
             if constexpr ((FAM & 1) != 0) {
                 if (fx[0] || (fu[0] && HASU)) {  // warp-uniform
-                    constexpr int SL = Cfg::fslot(0);
+                    constexpr int FSEL_ = 0;
                     T gf[NI][RX], sx[NI][RX], yf[NI][RU], su[NI][RU];
 #pragma unroll
                     for (int j = 0; j < NI; ++j) {
-                        lds_piece<T, RX, SX>(bx + ((3 + SL) * NI + j) * PXB, gf[j]);
-                        lds_piece<T, RU, SU>(bu + ((4 + SL) * NI + j) * PUB, yf[j]);
+                        lds_piece<T, RX, CX>(bx + (unsigned)(REC::gf(FSEL_) + j * JX) * ES, gf[j]);
+                        lds_piece<T, RU, CU>(bu + (unsigned)(REC::yf(FSEL_) + j * JU) * ES, yf[j]);
 #pragma unroll
                         for (int a = 0; a < RX; ++a) sx[j][a] = xo[j][a] + gf[j][a];
 #pragma unroll
@@ -811,8 +892,8 @@ __global__ void __launch_bounds__(GPS_MAX_WARPS * 32, 1)
                 xr[j] += NX;
                 ur[j] += NU;
             }
-            sb = (sb + STAGE == S * STAGE) ? 0u : sb + STAGE;
-            sbi = (sbi + STAGE == S * STAGE) ? 0u : sbi + STAGE;
+            sc = (sc + 1 == S) ? 0 : sc + 1;
+            si = (si + 1 == S) ? 0 : si + 1;
         };
         for (int k = 0; k < N - 1; ++k) column(k, true);
         column(N - 1, false);
@@ -822,31 +903,33 @@ __global__ void __launch_bounds__(GPS_MAX_WARPS * 32, 1)
     auto backward = [&]() {
         T mS1b[RX + RU][NX], mKt[RX][NU], mQuu[RU][NU], vAPf[RX], vBPf[RU];
         load_bwd_rows(mS1b, mKt, mQuu, vAPf, vBPf);
-        T *cx = px0 + (int64_t)(N - 1) * recA, *cu = pu0 + (int64_t)(N - 1) * recA;  // record of the current knot point
+        T *cu = pu0 + (int64_t)(N - 1) * recA;  // this lane's input rows in the record of the current knot point
+        sweep_fence();
 #pragma unroll
-        for (int t = 0; t < DB; ++t) issue_bwd(N - 1 - t, t, cx - t * recA, cu - t * recA);
+        for (int t = 0; t < DB; ++t) issue_bwd(N - 1 - t, t);
         int tc = 0, ti = DB % BS;  // ring stage of the current step / of the step being fetched
         T po[NI][RX], Pf[NI][NX];
         {   // terminal cost p_{N-1}
-            issue_bwd(N - 1 - DB, ti, cx - DB * recA, cu - DB * recA);
-            cp_wait_c<DB>();
+            issue_bwd(N - 1 - DB, ti);
+            bulk_wait(tc);
+            const unsigned ox = xvl ? aRing + (unsigned)tc * IMGB + lxo : aZero;
 #pragma unroll
-            for (int j = 0; j < NI; ++j) lds_piece<T, RX, SX>(aXl + bwd_off_x(tc) + j * PXB, po[j]);
+            for (int j = 0; j < NI; ++j) lds_piece<T, RX, CX>(ox + (unsigned)(j * JX) * ES, po[j]);
             gather_x(po, Pf);
-            cx -= recA;
             cu -= recA;
             tc = (tc + 1 == BS) ? 0 : tc + 1;
             ti = (ti + 1 == BS) ? 0 : ti + 1;
         }
         for (int k = N - 2; k >= 0; --k) {
-            issue_bwd(k - DB, ti, cx - DB * recA, cu - DB * recA);
-            cp_wait_c<DB>();
+            issue_bwd(k - DB, ti);
+            bulk_wait(tc);
             T q[NI][RX], r[NI][RU], Rf[NI][NU];
-            const unsigned ox = aXl + bwd_off_x(tc), ou = aUl + bwd_off_u(tc);
+            const unsigned ox = xvl ? aRing + (unsigned)tc * IMGB + lxo : aZero;
+            const unsigned ou = uvl ? aRing + (unsigned)tc * IMGB + luo : aZero;
 #pragma unroll
             for (int j = 0; j < NI; ++j) {
-                lds_piece<T, RX, SX>(ox + j * PXB, q[j]);
-                lds_piece<T, RU, SU>(ou + j * PUB, r[j]);
+                lds_piece<T, RX, CX>(ox + (unsigned)(j * JX) * ES, q[j]);
+                lds_piece<T, RU, CU>(ou + (unsigned)(REC::r - REC::q + j * JU) * ES, r[j]);
             }
             gather_u(r, Rf);
             // d_k = Quu_inv ((B^T p_{k+1} + r_k) + BPf)
@@ -873,7 +956,6 @@ __global__ void __launch_bounds__(GPS_MAX_WARPS * 32, 1)
                 dots<FAST>(mQuu, Sf[j], dq);
                 stg_piece<T, RU, CU>(cu + REC::d + j * JU, dq, puv);
             }
-            cx -= recA;
             cu -= recA;
             tc = (tc + 1 == BS) ? 0 : tc + 1;
             ti = (ti + 1 == BS) ? 0 : ti + 1;
@@ -1185,10 +1267,11 @@ inline GpsPlan gps_plan_L(const LaunchDesc &d) {
     p.ly.has_b = (s.v || s.z || s.vcnew || s.zcnew || s.vlnew || s.zlnew || s.vlnew_tv || s.zlnew_tv) ? 1 : 0;
     const int max_smem = d.max_smem_optin - 64;
     const size_t blob = ((size_t)(3 * NX * NX + 2 * NX * NU + NU * NU + 4 * NX + 2 * NU) * sizeof(T) + 15) / 16 * 16;
-    const size_t per_warp = Cfg::WARP_BYTES;
-    if (blob + per_warp > (size_t)max_smem) return p;
-    int maxw = (int)std::min<size_t>(GPS_MAX_WARPS, ((size_t)max_smem - blob) / per_warp);
-    maxw = std::max(1, std::min(maxw, std::max(1, gps_env_int("TINYMPC_GPS_WARPS", GPS_MAX_WARPS))));
+    using RINGH = GpsRing<NX, NU, L, (int)sizeof(T), NI, FAM>;
+    const size_t per_warp = RINGH::WARP_BYTES, fixed = blob + RINGH::ZERO_BYTES;
+    if (fixed + per_warp > (size_t)max_smem) return p;
+    int maxw = (int)std::min<size_t>(gps_max_warps(NI), ((size_t)max_smem - fixed) / per_warp);
+    maxw = std::max(1, std::min(maxw, std::max(1, gps_env_int("TINYMPC_GPS_WARPS", gps_max_warps(NI)))));
     // balance the waves: with `waves` passes over the resident slots, use just enough warps per SM to hold B / waves
     const int64_t groups = (d.io.B + SPW - 1) / SPW;  // warps' worth of instances
     const int64_t cap = (int64_t)d.sm_count * maxw;
@@ -1198,7 +1281,7 @@ inline GpsPlan gps_plan_L(const LaunchDesc &d) {
     p.NI = NI;
     p.warps = warps;
     p.ctas = (int)std::max<int64_t>(1, std::min<int64_t>(d.sm_count, (groups + warps - 1) / warps));
-    p.smem = blob + per_warp * (size_t)warps;
+    p.smem = fixed + per_warp * (size_t)warps;
     p.ws_bytes = (size_t)p.ctas * warps * d.N * (REC::recA + (p.ly.has_b ? REC::recB : 0)) * sizeof(T);
     return p;
 }

@@ -203,17 +203,27 @@ int resolve_family(const tinympc_b200_solver *s, const Features &ft, int *smem_o
     if (s->family == TINYMPC_KERNEL_GPI) return gpi_ok ? TINYMPC_KERNEL_GPI : (gps_ok ? TINYMPC_KERNEL_GPS : -1);
     if (s->family == TINYMPC_KERNEL_GPS) return gps_ok ? TINYMPC_KERNEL_GPS : -1;
     if (s->family == TINYMPC_KERNEL_TPI) return TINYMPC_KERNEL_TPI;
-    // AUTO
-    if (ft.ext) return gps_ok ? TINYMPC_KERNEL_GPS : TINYMPC_KERNEL_TPI;  // measured: profiles/r02_* (rocket landing, 3-4x)
-    if (!gpi_ok) return TINYMPC_KERNEL_TPI;
-    // GPI unless on-chip memory (shared + tensor memory) holds fewer than 32 instances per SM (long horizons with
-    // wide inputs) AND the batch is large enough to fill the GPU with one thread per instance.  Measured on B200
-    // (profiles/r01_sweep_1gpu.md, B = 131 072, N = 100): at 16 instances/SM TPI wins by 10-35 % for every shape except
-    // (16,8), where its register footprint costs more than the low GPI occupancy; at >= 32 instances/SM GPI always wins.
+    // AUTO (measured rules; evidence: profiles/r02_auto_rule_sweep.md, profiles/r01_sweep_1gpu.md)
+    const int gps_plan = gps_ok ? s->dim->gps_lanes(s->dtype) : 0;
+    const bool gps_two = ((gps_plan >> 8) & 0xff) == 2;  // two instances per lane group: the small shapes
+    const bool big_batch = B >= (int64_t)s->sm_count * 384;  // one thread per instance fills the GPU
+    // cones / hyperplanes: streamed lane groups (rocket landing, fp64: 3.3x the thread-per-instance kernel)
+    if (ft.ext) return gps_ok ? TINYMPC_KERNEL_GPS : TINYMPC_KERNEL_TPI;
+    // box constraints, streamed alternative when the state does not stay on chip: for big batches the streamed lane groups
+    // beat one thread per instance on the small fp64 shapes ((6,3,100): 28.1 vs 36.7 ms, (4,2,50): 9.1 vs 11.6 ms) and lose
+    // on the wide ones ((12,4,50) fp64: 61.6 vs 35.8 ms; fp32 N = 100: 41-113 vs 36-71 ms); small batches cannot fill the
+    // GPU with one thread per instance
+    const int streamed = !gps_ok ? TINYMPC_KERNEL_TPI
+                                 : ((!big_batch || (s->dtype == TINYMPC_F64 && gps_two)) ? TINYMPC_KERNEL_GPS : TINYMPC_KERNEL_TPI);
+    if (!gpi_ok) return streamed;
+    // on chip (GPI) unless shared + tensor memory hold fewer than 32 instances per SM (long horizons with wide inputs, fp64)
+    // AND the batch is large.  Measured on B200 (B = 131 072, N = 100): at 16 instances/SM the streamed kernels win by 10-35 %
+    // for every shape except (16,8), where the thread-per-instance register footprint costs more than the low on-chip
+    // occupancy; at >= 32 instances/SM GPI always wins.
     const int plan = s->dim->gpi_instances_per_cta ? s->dim->gpi_instances_per_cta(s->dtype, s->N, s->max_smem_optin) : 0;
     const int ipc = plan & 0xffff;
-    const bool tpi_heavy = s->nx >= 16 && s->nu >= 8;
-    if (ipc > 0 && ipc < 32 && !tpi_heavy && B >= (int64_t)s->sm_count * 384) return TINYMPC_KERNEL_TPI;
+    const bool tpi_heavy = s->nx >= 16 && s->nu >= 8 && s->dtype == TINYMPC_F32;
+    if (ipc > 0 && ipc < 32 && !tpi_heavy && big_batch) return streamed;
     return TINYMPC_KERNEL_GPI;
 }
 

@@ -179,8 +179,17 @@ extern "C" int TM_SYM(tm_gps_launch_)(tmpc::LaunchDesc *d) {
 }
 // lanes per instance of the streamed lane-group kernel for this shape (0 = not available)
 extern "C" int TM_SYM(tm_gps_lanes_)(int dtype) {
-    if (dtype == TINYMPC_F32) return tmpc::gps_pick_L<float, TM_NX, TM_NU>();
-    if (dtype == TINYMPC_F64) return tmpc::gps_pick_L<double, TM_NX, TM_NU>();
+    // lanes per instance in bits 0-7, instances per lane group (1 or 2) in bits 8-15
+    if (dtype == TINYMPC_F32) {
+        constexpr int Lf = tmpc::gps_pick_L<float, TM_NX, TM_NU>();
+        if constexpr (Lf == 0) return 0;
+        else return Lf | (tmpc::gps_pick_NI<float, TM_NX, TM_NU, Lf>() << 8);
+    }
+    if (dtype == TINYMPC_F64) {
+        constexpr int Ld = tmpc::gps_pick_L<double, TM_NX, TM_NU>();
+        if constexpr (Ld == 0) return 0;
+        else return Ld | (tmpc::gps_pick_NI<double, TM_NX, TM_NU, Ld>() << 8);
+    }
     return 0;
 }
 #endif

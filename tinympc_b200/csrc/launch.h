@@ -65,7 +65,7 @@ struct DimEntry {
     // batched cache precompute on the device (precompute_kernel.cuh): device pointers, one model blob per instance
     int (*precompute_batch)(int dtype, int64_t B, const void *A, const void *Bm, const void *f, const void *Qdiag, const void *Rdiag,
                             const void *rho, void *models_out, int32_t *sweeps_out, int sm_count, cudaStream_t stream);
-    // streamed lane-group kernel (gps_kernel.cuh): lanes per instance for this dtype, 0 = shape not available
+    // streamed lane-group kernel (gps_kernel.cuh): lanes per instance (bits 0-7) | instances per lane group << 8; 0 = shape not available
     int (*gps_lanes)(int dtype);
 };
 

@@ -23,11 +23,14 @@ FAM = {"gpi": abi.KERNEL_GPI, "gps": abi.KERNEL_GPS, "tpi": abi.KERNEL_TPI, "aut
 NAMES = {1: "tpi", 2: "gpi", 4: "gps"}
 shapes = [(np.float32, 4, 8, 100), (np.float32, 8, 8, 100), (np.float32, 12, 4, 100), (np.float32, 12, 8, 100), (np.float32, 16, 4, 100),
           (np.float32, 16, 8, 100), (np.float32, 12, 8, 50), (np.float32, 16, 8, 50), (np.float32, 12, 4, 50),
-          (np.float64, 12, 4, 50), (np.float64, 6, 3, 100), (np.float64, 4, 2, 50), (np.float64, 16, 8, 50)]
+          (np.float64, 12, 4, 50), (np.float64, 6, 3, 100), (np.float64, 4, 2, 50), (np.float64, 16, 8, 50),
+          # small batches (one thread per instance cannot fill the GPU)
+          (np.float64, 12, 4, 50, 4096), (np.float32, 12, 8, 100, 4096), (np.float32, 16, 4, 100, 8192), (np.float64, 8, 4, 50, 16384)]
 print("| dtype | nx | nu | N | B | family asked | ran | plan | ms | ADMM it/s |")
 print("|---|---|---|---|---|---|---|---|---|---|")
-for dt, nx, nu, N in shapes:
-    B = a.B if dt == np.float32 else a.B // 2
+for shp in shapes:
+    dt, nx, nu, N = shp[:4]
+    B = shp[4] if len(shp) > 4 else (a.B if dt == np.float32 else a.B // 2)
     spec = wl.random_lti(nx, nu, N, seed=1)
     spec.settings.abs_pri_tol = 0.0
     spec.settings.abs_dua_tol = 0.0

@@ -62,7 +62,8 @@ def row(name, spec, dt, inst, B, kernel, kname, mode, mname, per_inst_ref):
     es = np.dtype(dt).itemsize
     gbs = B * bytes_inst(spec.nx, spec.nu, spec.N, es, per_inst_ref) / (ms * 1e-3) / 1e9
     tf = iters * flops_iter(spec.nx, spec.nu, spec.N) / (ms * 1e-3) / 1e12
-    fam = {1: "tpi", 2: f"gpi L={st['lanes_per_instance']} {st['instances_per_cta']}/SM" + (" tmem" if st["tmem_cols_per_cta"] else ""), 3: "hybrid"}[st["kernel_family"]]
+    lanes, ipc = st["lanes_per_instance"], st["instances_per_cta"]
+    fam = {1: "tpi", 2: f"gpi L={lanes} {ipc}/SM" + (" tmem" if st["tmem_cols_per_cta"] else ""), 4: f"gps L={lanes} {ipc}/SM"}[st["kernel_family"]]
     print(f"| {name} | {spec.nx} | {spec.nu} | {spec.N} | {B} | {np.dtype(dt).name} | {fam} | {mname} | {ms:.3f} | {B / ms * 1e3:.3e} | "
           f"{iters / ms * 1e3:.3e} | {solved / B:.2f} | {gbs:.1f} | {gbs / HBM:.5f} | {tf:.2f} |", flush=True)
 
@@ -76,6 +77,7 @@ row("C2 hovering", spec, np.float32, wl.hovering_instances(65536, N=50), 65536, 
 row("C3 tracking", spec, np.float32, wl.tracking_instances(65536, N=50, seed=0), 65536, abi.KERNEL_GPI, "gpi", S, "strict", True)
 row("C3 tracking", spec, np.float32, wl.tracking_instances(65536, N=50, seed=0), 65536, abi.KERNEL_TPI, "tpi", S, "strict", True)
 spec = wl.rocket(N=100)
+row("C4 rocket+SOC", spec, np.float64, wl.rocket_instances(16384, N=100, seed=0), 16384, abi.KERNEL_AUTO, "auto", S, "strict", False)
 row("C4 rocket+SOC", spec, np.float64, wl.rocket_instances(16384, N=100, seed=0), 16384, abi.KERNEL_TPI, "tpi", S, "strict", False)
 # config 5 sweep (fixed work)
 for nx in (4, 8, 12, 16):

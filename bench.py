@@ -159,7 +159,7 @@ def host_cores():
 # CPU arm: the reference's own implementation on the host cores (oracle/_ref), or the oracle port
 # ---------------------------------------------------------------------------------------------------------
 def cpu_case(case, steps, warmup, per_thread, cores):
-    """Times the reference on a bounded sample of `case` -> dict(value inst/s, iters_per_s, one_thread, per_core, ...)."""
+    """Times the reference on a bounded sample (the first instances) of `case` -> dict(value inst/s, iters_per_s, one_thread, ...)."""
     from oracle import oracle
     from tinympc_b200.batch import HostBatch
 
@@ -248,7 +248,7 @@ def reference_main(args, rank, world):
         return
     cores = host_cores()
     W = max(1, args.warmup)
-    c2 = cpu_case(make_case("C2", B=max(args.cpu_per_thread * cores["effective"], 1024)), args.steps, W, args.cpu_per_thread, cores)
+    c2 = cpu_case(make_case("C2"), args.steps, W, args.cpu_per_thread, cores)
     cb = cpu_summary(c2, cores)
     line = {
         "impl": "reference", "metric": METRIC, "value": c2["value"], "unit": "instances/s", "n_gpus": args.gpus,
@@ -264,7 +264,7 @@ def reference_main(args, rank, world):
         cfgs = {}
         for name in EXTRA_CASES:
             try:
-                case = make_case(name, B=max(args.cpu_per_thread * cores["effective"], 1024))
+                case = make_case(name)  # the GPU arm's batch (same generator, same seed): the sample is its first instances
                 c = cpu_case(case, 2, 1, args.cpu_per_thread, cores)
                 cfgs[name] = {"workload": case["label"], "dtype": np.dtype(case["dtype"]).name, "ms_per_step": c["ms_per_step"],
                               "cpu_reference": cpu_summary(c, cores), "value": c["value"], "unit": "instances/s"}
@@ -589,10 +589,10 @@ def main():
         try:
             cores = cores_before
             pt = args.cpu_per_thread
-            c2 = cpu_case(make_case("C2", B=max(pt * cores["effective"], 1024)), 2, 1, pt, cores)
+            c2 = cpu_case(make_case("C2"), 2, 1, pt, cores)
             line["cpu_baseline"] = cpu_summary(c2, cores)
             for name in cfgs:
-                cc = cpu_case(make_case(name, B=max(pt * cores["effective"], 1024)), 1, 1, pt, cores)
+                cc = cpu_case(make_case(name), 1, 1, pt, cores)
                 cfgs[name]["cpu_reference"] = cpu_summary(cc, cores)
         except Exception as e:  # the checker libraries are optional for the product arm
             line["cpu_baseline"] = {"value": None, "unit": "instances/s", "cores": os.cpu_count(), "kind": "unavailable", "sample": str(e)[:200]}

@@ -604,3 +604,28 @@ def test_closed_loop_without_previous_slacks_equals_reference_with_v_z_zeroed():
             assert H.bits_equal(out[key].cpu().numpy(), o[key]), (k, key)
         state = {n: o[n] for n in H.BOX_STATE}
         x0 = loop.x0.cpu().numpy().copy()  # the plant update itself is covered by test_device_resident_closed_loop_matches_oracle
+
+
+@pytest.mark.parametrize("kernel", ALLK)
+def test_bounds_with_signed_zeros(kernel):
+    """Bounds that contain +0 / -0: Eigen's compare-select clamp and min / max instructions differ in the SIGN of a zero
+    result there, so the on-chip kernel must fall back to the compare-select form (it uses min / max only when no bound is
+    a zero).  Inputs are chosen so that slacks land exactly on the zero bounds."""
+    spec = wl.quadrotor(N=10)
+    dt = np.float32
+    spec.constraints = dict(x_min=np.array([-5, -5, 0.0, -5, -5, -5, -0.0, -5, -5, -5, -5, -5]), x_max=np.array([5, 5, 5, 5, -0.0, 5, 5, 5, 5, 5, 0.0, 5]),
+                            u_min=np.array([-0.0, -0.5, 0.0, -0.5]), u_max=np.array([0.5, 0.0, 0.5, -0.0]))
+    prob = setup_problem(spec, dt)
+    st = abi.Settings.from_buffer_copy(spec.settings)
+    st.max_iter = 25
+    B = 77
+    inst = wl.tracking_instances(B, N=10, seed=9, dtype=dt)
+    inst["x0"][: B // 2] = -inst["x0"][: B // 2]
+    solver = _mk_solver(prob, st, kernel)
+    want = tuple(H.BOX_STATE)
+    g = solver.solve(inst["x0"], inst["Xref"], None, cold_start=True, want_state=want)
+    o = _port(prob, st, inst["x0"], inst["Xref"], None, None, True, want)
+    for key in H.OUT_KEYS + H.BOX_STATE:
+        assert H.bits_equal(g[key], o[key]), (kernel, key)
+    z = o["znew"]
+    assert (z == 0).any() and np.signbit(z[z == 0]).any() and (~np.signbit(z[z == 0])).any()  # both zero signs occur

@@ -128,6 +128,7 @@ struct tinympc_b200_solver {
     // device copies
     DevBuf d_xmin, d_xmax, d_umin, d_umax, d_blob;
     int bounds_tv = 0;
+    int bounds_zero_free = 1;
     DevBuf d_Alin_x, d_blin_x, d_Alin_u, d_blin_u, d_tvA_x, d_tvb_x, d_tvA_u, d_tvb_u;
     tinympc_settings_t settings;
     int mode = TINYMPC_MODE_STRICT;
@@ -287,6 +288,7 @@ void base_desc(const tinympc_b200_solver *s, tmpc::LaunchDesc &d, const Features
     d.tv_Alin_x = s->d_tvA_x.p; d.tv_blin_x = s->d_tvb_x.p; d.tv_Alin_u = s->d_tvA_u.p; d.tv_blin_u = s->d_tvb_u.p;
     d.gmat = s->d_blob.p;
     d.bounds_tv = s->bounds_tv;
+    d.bounds_zero_free = s->bounds_zero_free;
     d.h_xlo = s->h_xlo.empty() ? nullptr : s->h_xlo.data(); d.h_xhi = s->h_xhi.empty() ? nullptr : s->h_xhi.data();
     d.h_ulo = s->h_ulo.empty() ? nullptr : s->h_ulo.data(); d.h_uhi = s->h_uhi.empty() ? nullptr : s->h_uhi.data();
     d.sm_count = s->sm_count;
@@ -603,6 +605,14 @@ int tinympc_b200_create(const tinympc_problem_t *p, int32_t device, tinympc_b200
             if (std::memcmp(c, c + k * rows * es, rows * es) != 0) return true;
         return false;
     };
+    auto has_zero = [&](const void *m, size_t n) {  // any element == +-0 ?
+        if (!m) return false;
+        for (size_t i = 0; i < n; ++i)
+            if ((es == 8 ? ((const double *)m)[i] : (double)((const float *)m)[i]) == 0.0) return true;
+        return false;
+    };
+    s->bounds_zero_free = !(has_zero(p->x_min, (size_t)nx * N) || has_zero(p->x_max, (size_t)nx * N) ||
+                            has_zero(p->u_min, (size_t)nu * (N - 1)) || has_zero(p->u_max, (size_t)nu * (N - 1)));
     s->bounds_tv = varies(p->x_min, nx, N) || varies(p->x_max, nx, N) || varies(p->u_min, nu, N - 1) || varies(p->u_max, nu, N - 1);
     if (p->x_min && p->x_max) {
         ok &= !upload(s->d_xmin, p->x_min, es * nx * N) && !upload(s->d_xmax, p->x_max, es * nx * N);

@@ -36,12 +36,13 @@ struct GpiCfg {
     static constexpr int NPV = PVP / W;     // vectors per pack
     static constexpr int NXP = (L * RX + W - 1) / W * W;  // gather buffer width (state vectors)
     static constexpr int NUP = (L * RU + W - 1) / W * W;  // gather buffer width (input vectors)
-    static constexpr int GBUF = IPW * (NXP > NUP ? NXP : NUP);
+    static constexpr int GBUF1 = IPW * (NXP > NUP ? NXP : NUP);  // one gather buffer
+    static constexpr int GBUF = 3 * GBUF1;  // tensor-memory variant: three of them, each hot call site owns one (see gather_x)
     // registers needed for the per-lane matrix rows (in elements of T)
     static constexpr int MAT_REGS = RX * (2 * NX + 2 * NU + 3) + RU * (2 * NX + NU + 2);
     // shared-memory elements per warp for horizon N: primal pack + dual pack per (k, lane), d, gather scratch
     __host__ __device__ static constexpr size_t warp_elems(int N) {
-        return (size_t)N * 32 * PVP * 2 + (size_t)(N - 1) * RU * 32 + GBUF;
+        return (size_t)N * 32 * PVP * 2 + (size_t)(N - 1) * RU * 32 + GBUF1;  // shared memory is the constraint here: one gather buffer
     }
     // TMEM variant (fp32): the dual pack and d live in tensor memory, CPK 32-bit columns per knot point in the
     // lane of the owning thread; shared memory keeps the primal pack and the gather scratch
@@ -131,6 +132,10 @@ template <bool B>
 struct BoolTag {
     static constexpr bool value = B;
 };
+template <int J>
+struct IntTag {
+    static constexpr int value = J;
+};
 
 // Box clamp.  STRICT keeps Eigen's compare-select form (differs from fmax/fmin only in the sign of a zero
 // result when a bound is a signed zero); FAST uses the single-instruction min/max.
@@ -151,7 +156,9 @@ __device__ __forceinline__ double absmax(double m, double d) {
     return (a > m) ? a : m;
 }
 
-template <typename T, int NX, int NU, int L, bool FAST, bool HET, bool TM>
+// MM (STRICT only): the box clamp as min / max instructions.  Identical to Eigen's compare-select form for every input
+// (NaN included: both return the bound) except when a bound is a signed zero - the host sets MM only when no bound is +-0.
+template <typename T, int NX, int NU, int L, bool FAST, bool HET, bool TM, bool MM = false>
 __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
     gpi_solve_kernel(const __grid_constant__ KParams<T, NX, NU> P, const T *__restrict__ gmat, unsigned long long *queue) {
     using Cfg = GpiCfg<NX, NU, L, (int)sizeof(T)>;
@@ -368,30 +375,36 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
         }
     };
     // all-gather inside the lane group through shared memory: every lane stores its R values, then reads the
-    // whole vector with 16-byte broadcast loads (absolute row order -> ascending-k dot products as in the oracle)
-    auto gather_x = [&](const T (&own)[RX], T (&full)[NX]) {
-        __syncwarp();
+    // whole vector with 16-byte broadcast loads (absolute row order -> ascending-k dot products as in the oracle).
+    // There are three gather buffers; every call site of the sweeps owns one (BUF) such that two consecutive uses of a
+    // buffer always have another gather's barrier between them: the barrier that would protect the buffer's previous
+    // readers before it is overwritten (LEAD) is then unnecessary, one __syncwarp per gather instead of two.
+    // (the all-shared-memory variant has no room for three buffers in its fourth warp: one buffer, both barriers)
+    constexpr bool G3 = TM;
+    constexpr unsigned GB0 = 0u, GB1 = G3 ? (unsigned)Cfg::GBUF1 * ES : 0u, GB2 = G3 ? 2u * (unsigned)Cfg::GBUF1 * ES : 0u;
+    auto gather_x = [&](const unsigned bo, const bool LEAD, const T (&own)[RX], T (&full)[NX]) {  // always inlined with literals
+        if (LEAD || !G3) __syncwarp();
 #pragma unroll
-        for (int a = 0; a < RX; ++a) sts(aGB + (unsigned)(slot * NXP + l * RX + a) * ES, own[a]);
+        for (int a = 0; a < RX; ++a) sts(aGB + bo + (unsigned)(slot * NXP + l * RX + a) * ES, own[a]);
         __syncwarp();
 #pragma unroll
         for (int c = 0; c < NXP / W; ++c) {
             T t[W];
-            ldsv(aGB + (unsigned)(slot * NXP + c * W) * ES, t);
+            ldsv(aGB + bo + (unsigned)(slot * NXP + c * W) * ES, t);
 #pragma unroll
             for (int e = 0; e < W; ++e)
                 if (c * W + e < NX) full[c * W + e] = t[e];
         }
     };
-    auto gather_u = [&](const T (&own)[RU], T (&full)[NU]) {
-        __syncwarp();
+    auto gather_u = [&](const unsigned bo, const bool LEAD, const T (&own)[RU], T (&full)[NU]) {
+        if (LEAD || !G3) __syncwarp();
 #pragma unroll
-        for (int b = 0; b < RU; ++b) sts(aGB + (unsigned)(slot * NUP + l * RU + b) * ES, own[b]);
+        for (int b = 0; b < RU; ++b) sts(aGB + bo + (unsigned)(slot * NUP + l * RU + b) * ES, own[b]);
         __syncwarp();
 #pragma unroll
         for (int c = 0; c < NUP / W; ++c) {
             T t[W];
-            ldsv(aGB + (unsigned)(slot * NUP + c * W) * ES, t);
+            ldsv(aGB + bo + (unsigned)(slot * NUP + c * W) * ES, t);
 #pragma unroll
             for (int e = 0; e < W; ++e)
                 if (c * W + e < NU) full[c * W + e] = t[e];
@@ -481,7 +494,7 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
         T xo[RX], Xf[NX];
 #pragma unroll
         for (int a = 0; a < RX; ++a) xo[a] = x0o[a];
-        gather_x(xo, Xf);
+        gather_x(GB1, false, xo, Xf);
         // one column: slack + dual update of this lane's rows, residual maxima; HASU = the column has inputs
         auto column = [&](int k, const bool HASU, const T (&u)[RU], const T (&vprev)[PVP], const T (&pb)[PVP]) {  // always inlined with a literal HASU
             T pa[PVP], na[PVP], nb[PVP];
@@ -560,7 +573,7 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
                 }
                 vadd<T, PVP>(X, pb, sum);
 #pragma unroll
-                for (int e = 0; e < PVP; ++e) v[e] = (e < RX + RU) ? clamp_box<FAST>(sum[e], lo[e], hi[e]) : sum[e];
+                for (int e = 0; e < PVP; ++e) v[e] = (e < RX + RU) ? clamp_box<FAST || MM>(sum[e], lo[e], hi[e]) : sum[e];
                 vsub<T, PVP>(sum, v, dg);
                 vsub<T, PVP>(X, v, dx);
                 vsub<T, PVP>(vo, v, dv);
@@ -630,7 +643,7 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
             pb_ready(pbk);
 #pragma unroll
             for (int b = 0; b < RU; ++b) u[b] = (-t1[RX + b]) - dk[b];  // u_k = -(Kinf x_k) - d_k
-            gather_u(u, Uf);
+            gather_u(GB0, false, u, Uf);
             column(k, true, u, vprev, pbk);
             dots<FAST>(mB, Uf, bu);
             {   // x_{k+1} = (A x_k + B u_k) + f
@@ -640,7 +653,7 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
                 vadd<T, RX>(ax, bu, tx);
                 vadd<T, RX>(tx, vf, xo);
             }
-            gather_x(xo, Xf);
+            gather_x(GB1, false, xo, Xf);
         }
         {
             T udummy[RU], vprev[PVP], pbk[PVP];
@@ -923,7 +936,7 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
             T xo0[RX], Xf0[NX], t10[RX + RU];
 #pragma unroll
             for (int a = 0; a < RX; ++a) xo0[a] = x0o[a];
-            gather_x(xo0, Xf0);
+            gather_x(GB1, true, xo0, Xf0);
             T d0[RU];
             load_d(0, d0);
             dots<FAST>(mS1f, Xf0, t10);
@@ -944,7 +957,7 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
             T xo[RX], Xf[NX];
 #pragma unroll
             for (int a = 0; a < RX; ++a) xo[a] = x0o[a];
-            gather_x(xo, Xf);
+            gather_x(GB1, false, xo, Xf);
             for (int k = 0; k < N; ++k) {
                 T na[PVP];
 #pragma unroll
@@ -961,13 +974,13 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
                         u[b] = (-t1[RX + b]) - dk[b];
                         na[RX + b] = u[b];
                     }
-                    gather_u(u, Uf);
+                    gather_u(GB0, false, u, Uf);
                     dots<FAST>(mB, Uf, bu);
 #pragma unroll
                     for (int a = 0; a < RX; ++a) xo[a] = (t1[a] + bu[a]) + vf[a];
                 }
                 if (slot == s) store_pack(aPA, k, na);
-                if (k < N - 1) gather_x(xo, Xf);
+                if (k < N - 1) gather_x(GB1, true, xo, Xf);
             }
             __syncwarp();
             if (P.s_x)
@@ -1029,7 +1042,7 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
 #pragma unroll
             for (int a = 0; a < RX; ++a) po[a] = nmac<FAST>(pterm[a], rho_(), pa[a] - pb[a]);
         }
-        gather_x(po, Pf);
+        gather_x(GB1, false, po, Pf);
         T q[RX], r[RU], Rf[NU];
         const T *xp = xrefp + (int64_t)(N - 2) * NX;
         const T *up = urefp + (has_uref ? (int64_t)(N - 2) * NU : 0);
@@ -1039,7 +1052,7 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
             pb_ready(pb);
             cost_eval(xr, ur, pa, pb, q, r);
         }
-        gather_u(r, Rf);
+        gather_u(GB2, false, r, Rf);
         // one backward step; MORE = another column follows (its cost inputs are fetched now and consumed at the end of
         // the step).  The last step (k = 0) is peeled so that the loop body carries no k > 0 predicates.
         auto bwd_step = [&](int k, const bool MORE) {  // always inlined with a literal MORE
@@ -1054,7 +1067,7 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
             dots<FAST>(mS1b, Pf, acc1);  // [AmBKt p_{k+1} ; B^T p_{k+1}]
 #pragma unroll
             for (int b = 0; b < RU; ++b) s_[b] = (acc1[RX + b] + r[b]) + vBPf[b];
-            gather_u(s_, Sf);
+            gather_u(GB0, false, s_, Sf);
             // p_k = ((q_k + AmBKt p_{k+1}) - Kinf^T r_k) + APf
             dots<FAST>(mKt, Rf, kr);
             {
@@ -1065,13 +1078,13 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
                 vsub<T, RX>(t1_, kr, t2_);
                 vadd<T, RX>(t2_, vAPf, po);
             }
-            if (MORE) gather_x(po, Pf);  // p_0 itself is never used (the forward pass starts from x_0)
+            if (MORE) gather_x(GB1, false, po, Pf);  // p_0 itself is never used (the forward pass starts from x_0)
             dots<FAST>(mQuu, Sf, dq);
             store_d(k, dq, busy);
             if (MORE) {
                 pb_ready(pb_n);
                 cost_eval(xr_n, ur_n, pa_n, pb_n, q, r);
-                gather_u(r, Rf);
+                gather_u(GB2, false, r, Rf);
             }
         };
         for (int k = N - 2; k >= 1; --k) bwd_step(k, true);
@@ -1177,10 +1190,10 @@ inline int gpi_fit_T(int N, int max_smem) {
     return (int)gpi_plan<T, NX, NU>(N, max_smem).smem;
 }
 
-template <typename T, int NX, int NU, int L, bool FAST, bool HET, bool TM>
+template <typename T, int NX, int NU, int L, bool FAST, bool HET, bool TM, bool MM = false>
 int launch_gpi_L(LaunchDesc *d, const GpiPlan &plan, const KParams<T, NX, NU> &P, const T *gmat) {
     if constexpr (gpi_feasible<T, NX, NU, L>() && (!TM || sizeof(T) == 4)) {
-        auto kern = gpi_solve_kernel<T, NX, NU, L, FAST, HET, TM>;
+        auto kern = gpi_solve_kernel<T, NX, NU, L, FAST, HET, TM, MM>;
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem) != cudaSuccess)
             return TINYMPC_ERR_CUDA;
         const int64_t ngroups = (d->io.B + (32 / L) - 1) / (32 / L);

@@ -105,8 +105,14 @@ int launch_gpi(LaunchDesc *d) {
     fill_params<T, NX, NU>(P, *d);
     const T *gmat = (const T *)d->gmat;
     const bool het = d->io.models != nullptr;  // heterogeneous batch: per-instance model blobs
-#define TM_GPI_CASE(LL, HH, TT) \
-    if (plan.L == LL && het == HH && plan.tm == TT) return launch_gpi_L<T, NX, NU, LL, FAST, HH, TT>(d, plan, P, gmat);
+    // STRICT, shared model, tensor-memory plan (the headline path): min / max clamp when no bound is a signed zero
+#define TM_GPI_CASE(LL, HH, TT)                                                                                          \
+    if (plan.L == LL && het == HH && plan.tm == TT) {                                                                    \
+        if constexpr (!FAST && !HH && TT && sizeof(T) == 4) {                                                            \
+            if (d->bounds_zero_free) return launch_gpi_L<T, NX, NU, LL, FAST, HH, TT, true>(d, plan, P, gmat);           \
+        }                                                                                                                \
+        return launch_gpi_L<T, NX, NU, LL, FAST, HH, TT>(d, plan, P, gmat);                                              \
+    }
 #define TM_GPI_L(LL) TM_GPI_CASE(LL, false, false) TM_GPI_CASE(LL, true, false) TM_GPI_CASE(LL, false, true) TM_GPI_CASE(LL, true, true)
     TM_GPI_L(4)
     TM_GPI_L(8)

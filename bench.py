@@ -511,14 +511,14 @@ def main():
     e2e_ok = bool(np.array_equal(hb.sol_u.view(np.uint8), out["sol_u"].cpu().numpy().view(np.uint8)))
     k_ms = float(np.mean(step_ms))  # one launch per step: the step IS the kernel
     roof = roofline(case, st, k_ms, iters_step, peak, peak_src)
-    traffic = None
+    traffic_table = {}
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(f"family{st['kernel_family']}_{args.mode}")
+            traffic_table = json.load(open(tpath))  # DRAM bytes per launch from the committed ncu captures
         except Exception:
-            traffic = None
-    roof["traffic"] = traffic
+            traffic_table = {}
+    roof["traffic"] = traffic_table.get(f"family{st['kernel_family']}_{args.mode}")
     roof["note"] = ("compute-bound by construction (SURVEY §8d: ~2000 flop per compulsory byte); the fp32-pipe / issue-slot "
                     "utilisation from ncu is the quality figure (profiles/r02_ncu_summary.md)")
     roof["flops_frac_of_74.5_tflops_fp32"] = roof["flops_achieved_tflops"] / 74.5
@@ -550,6 +550,7 @@ def main():
                      "iter_histogram_rank0": {str(i): n for i, n in enumerate(hist) if n},
                      "plan": plan_of(sx), "gpu_launches": Kx * sx["kernel_launches"],
                      "roofline": roofline(c, sx, kx, iters_x, peak, peak_src)}
+            entry["roofline"]["traffic"] = traffic_table.get(f"{name.split('_')[0].lower()}_family{sx['kernel_family']}_{args.mode}")
             extra_launches += Kx * sx["kernel_launches"]
             del b_, o_
             if name in ("C3", "C4"):

@@ -490,8 +490,8 @@ EXPECTED_F32_PLANS = {50: _P50, 100: _P100}
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
 @pytest.mark.parametrize("dims", ALL_DIMS)
 def test_launch_plans_long_horizons_vs_oracle(dims, dt, N):
-    """kernel = GPI (planner's choice) and AUTO on a ragged batch: cold solve + one warm-started solve, every scalar vs the
-    oracle.  fp32: the plan the bench tables quote is asserted through stats()."""
+    """kernel = GPI (planner's choice), AUTO and GPS on a ragged batch: cold solve + one warm-started solve, every scalar vs
+    the oracle.  fp32: the plan the bench tables quote is asserted through stats()."""
     nx, nu = dims
     spec = wl.random_lti(nx, nu, N, seed=7 * nx + nu)
     prob = setup_problem(spec, dt)
@@ -504,10 +504,12 @@ def test_launch_plans_long_horizons_vs_oracle(dims, dt, N):
     o1 = _port(prob, st, inst["x0"], inst["Xref"], None, None, True, want)
     x0b = (inst["x0"] * dt(0.9)).astype(dt)
     o2 = _port(prob, st, x0b, inst["Xref"], None, {n: o1[n].copy() for n in H.BOX_STATE}, False, want)
-    for kernel in ("gpi", "auto"):
+    for kernel in ("gpi", "auto", "gps"):  # "gps": the streamed lane groups (TMA record ring) at the long horizons too
         solver = _mk_solver(prob, st, kernel)
         g1 = solver.solve(inst["x0"], inst["Xref"], None, cold_start=True, want_state=want)
         stt = solver.stats()
+        if kernel == "gps":
+            assert stt["kernel_family"] == abi.KERNEL_GPS and stt["workspace_bytes"] > 0
         for key in H.OUT_KEYS + H.BOX_STATE:
             assert H.bits_equal(g1[key], o1[key]), (dims, N, kernel, key)
         g2 = solver.solve(x0b, inst["Xref"], None, state={n: g1[n].copy() for n in H.BOX_STATE}, cold_start=False, want_state=want)

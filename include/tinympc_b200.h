@@ -48,8 +48,8 @@ extern "C" {
 #define TINYMPC_KERNEL_GPI 2 /* lane-group-per-instance: state resident on chip (shared + tensor memory) when the   */
                              /* problem is box-constrained and fits, else the streamed variant below               */
 /* 3 was an experimental split of a batch between the GPI and TPI kernels; removed (it never won, see profiles/) */
-#define TINYMPC_KERNEL_GPS 4 /* lane-group-per-instance, state streamed through an L2/HBM workspace behind a       */
-                             /* cp.async ring (any feature set: box, cones, hyperplanes; fp32 and fp64)            */
+#define TINYMPC_KERNEL_GPS 4 /* lane-group-per-instance, state streamed through an L2/HBM workspace by TMA bulk     */
+                             /* copies (any feature set: box, cones, hyperplanes; fp32 and fp64)                   */
 
 /* error codes */
 #define TINYMPC_OK 0

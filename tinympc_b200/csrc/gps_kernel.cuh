@@ -1,5 +1,5 @@
 // gps_kernel.cuh — lane-group-per-instance batched ADMM solve with the N-indexed state STREAMED through a per-slot
-// workspace in global memory (L2 / HBM) behind a cp.async ring in shared memory ("GPS").
+// workspace in global memory (L2 / HBM) behind a ring of record images in shared memory filled by TMA bulk copies ("GPS").
 //
 // Same lane mapping as the on-chip kernel (gpi_kernel.cuh): L lanes form a group, lane l owns the state rows
 // [l*RX, (l+1)*RX) and the input rows [l*RU, (l+1)*RU); its rows of AmBKt / B^T / A / Kinf / Kinf^T / B / Quu_inv live
@@ -15,10 +15,12 @@
 //     one instance per group: 1.8 `wait` stalls per issued instruction, issue slots 39 % busy);
 //   * the per-instance state does not have to fit on chip (rocket landing, N = 100, fp64: 31 KB per instance): it lives
 //     in a workspace indexed by RESIDENT SLOT (not by instance), one record per (warp, knot point) laid out
-//     [field][slot of the warp][row], so that every field access of a warp is one contiguous run of bytes.  Each
-//     lane moves only its own rows: cp.async (4/8/16-byte chunks) into a private slice of a shared-memory ring
-//     `dist` steps ahead of their use, plain vector stores on the way out.  A lane only ever re-reads what it wrote
-//     itself, so program order is all the ordering the ring needs (no barriers, no drain at the sweep turnarounds);
+//     [field][slot of the warp][row].  A sweep step needs one contiguous block of the record, which ONE TMA bulk copy
+//     (cp.async.bulk, issued by lane 0, completion on a per-stage mbarrier) brings into a ring of record images several
+//     steps ahead of its use (GpsRing); every lane reads its own rows from the image and writes results back with
+//     predicated vector stores.  fence.proxy.async.global + __syncwarp at each sweep start order a sweep's stores before
+//     the next sweep's bulk copies; within a sweep a stage is only overwritten after a gather barrier that follows its last
+//     read.  Reference rows come straight into registers (ld.global.nc) behind an L2 prefetch;
 //   * the linear cost of the NEXT iteration (q_k, r_k, p_{N-1}; update_linear_cost, admm.cpp:262-304) is evaluated
 //     in the forward sweep, where the fresh slack / dual values are in registers, and stored: the backward sweep
 //     reads q, r (nx+nu values per knot point) instead of every slack / dual pair (up to 8 (nx+nu));
@@ -52,14 +54,7 @@ struct GpsCfg {
     static constexpr int CU = gps_gcd(16, gps_gcd(NU * ES, RU * ES));
     static constexpr int SX = gps_gcd(16, RX * ES);
     static constexpr int SU = gps_gcd(16, RU * ES);
-    // ring piece slots.  state-shaped: 0 vnew (backward: q), 1 g, 2 xref, 3.. family duals (compiled-in families only)
-    //                    input-shaped: 0 d (backward: r), 1 znew, 2 y, 3 uref, 4.. family duals
     static constexpr int NF = gps_popc(FAM);
-    static constexpr int XP = 3 + NF;
-    static constexpr int UP = 4 + NF;
-    static constexpr int PXB = 32 * RX * ES;  // bytes of one state-shaped piece slot (32 lanes, one instance of the group)
-    static constexpr int PUB = 32 * RU * ES;
-    static constexpr int STAGE_BYTES = NI * (XP * PXB + UP * PUB);
     // matrix rows a lane holds in registers during one sweep (elements): forward A, Kinf, B, Qd, f, Rd; backward AmBKt,
     // B^T, Kinf^T, Quu_inv, APf, BPf
     static constexpr int FWD_ROWS = (RX + RU) * NX + RX * NU + 2 * RX + RU;
@@ -67,9 +62,6 @@ struct GpsCfg {
     static constexpr int SWEEP_REGS = (FWD_ROWS > BWD_ROWS ? FWD_ROWS : BWD_ROWS) * (ES / 4);
     static constexpr bool ok = (NX % RX == 0) && (NU % RU == 0) && SWEEP_REGS <= 112;
     static constexpr int PARK_BYTES = 32 * NI * 2 * RX * ES;  // per-lane x0 rows and terminal-cost rows (kept out of registers)
-    static constexpr size_t WARP_BYTES = (size_t)(GBX + GBU) * ES + (size_t)PARK_BYTES + (size_t)3 * STAGE_BYTES;  // 3 = GPS_STAGES
-    // ring slot of family f's dual (f must be compiled in)
-    __host__ __device__ static constexpr int fslot(int f) { return gps_popc(FAM & ((1 << f) - 1)); }
 };
 
 // Record layout: one record per (warp, knot point), every field [slot of the warp][row] padded to 16 bytes.  Region A is
@@ -134,43 +126,6 @@ constexpr int gps_pick_NI() {
 // warps per CTA: one instance per lane group leaves room for twice the warps of the two-instance variant (registers)
 __host__ __device__ constexpr int gps_max_warps(int NI) { return NI == 1 ? 14 : 8; }
 
-// ---- cp.async (per-thread asynchronous global -> shared copies) ----
-template <int BYTES>
-__device__ __forceinline__ void cp_async(unsigned dst, const void *src) {
-    static_assert(BYTES == 4 || BYTES == 8 || BYTES == 16, "cp.async moves 4, 8 or 16 bytes");
-    if constexpr (BYTES == 16) {
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-    } else if constexpr (BYTES == 8) {
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
-    } else {
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
-    }
-}
-__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_wait(int pending) {  // warp-uniform argument
-    if (pending <= 0) asm volatile("cp.async.wait_group 0;" ::: "memory");
-    else if (pending == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
-    else if (pending == 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
-    else asm volatile("cp.async.wait_group 3;" ::: "memory");
-}
-template <int PENDING>
-__device__ __forceinline__ void cp_wait_c() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory");
-}
-// predicated forms (pr != 0: do it): one PTX predicate instead of a branch around the copy.  Lanes that own only padding
-// rows skip their copies / stores this way; a branch per guarded group cost 9 % of the kernel's instructions (BSSY / BRA /
-// BSYNC, ncu source view of the rocket-landing solve) and every reconvergence point is a scheduling barrier for ptxas.
-template <int BYTES>
-__device__ __forceinline__ void cp_async_p(unsigned dst, const void *src, unsigned pr) {
-    static_assert(BYTES == 4 || BYTES == 8 || BYTES == 16, "cp.async moves 4, 8 or 16 bytes");
-    if constexpr (BYTES == 16) {
-        asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %2, 0;\n @q cp.async.cg.shared.global [%0], [%1], 16;\n}" ::"r"(dst), "l"(src), "r"(pr) : "memory");
-    } else if constexpr (BYTES == 8) {
-        asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %2, 0;\n @q cp.async.ca.shared.global [%0], [%1], 8;\n}" ::"r"(dst), "l"(src), "r"(pr) : "memory");
-    } else {
-        asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %2, 0;\n @q cp.async.ca.shared.global [%0], [%1], 4;\n}" ::"r"(dst), "l"(src), "r"(pr) : "memory");
-    }
-}
 // predicated read-only global loads of a lane's rows into registers (pr == 0: the registers keep their zeros) and L2 prefetch
 __device__ __forceinline__ void ldg_chunk(const float *p, float (&v)[1], unsigned pr) {
     asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %2, 0;\n @q ld.global.nc.f32 %0, [%1];\n}" : "+f"(v[0]) : "l"(p), "r"(pr));
@@ -206,18 +161,6 @@ __device__ __forceinline__ void prefetch_l2(const void *p, unsigned pr) {
     asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %1, 0;\n @q prefetch.global.L2 [%0];\n}" ::"l"(p), "r"(pr));
 }
 
-// a lane's piece of PB bytes in chunks of CB bytes
-template <int PB, int CB>
-__device__ __forceinline__ void cp_piece(unsigned dst, const void *src) {
-#pragma unroll
-    for (int c = 0; c < PB / CB; ++c) cp_async<CB>(dst + (unsigned)(c * CB), reinterpret_cast<const char *>(src) + c * CB);
-}
-template <int PB, int CB>
-__device__ __forceinline__ void cp_piece(unsigned dst, const void *src, unsigned pr) {
-#pragma unroll
-    for (int c = 0; c < PB / CB; ++c) cp_async_p<CB>(dst + (unsigned)(c * CB), reinterpret_cast<const char *>(src) + c * CB, pr);
-}
-
 // ---- chunked piece moves between registers and shared / global memory ----
 __device__ __forceinline__ void lds_chunk(unsigned a, float (&v)[1]) { v[0] = lds(a, 0.f); }
 __device__ __forceinline__ void lds_chunk(unsigned a, float (&v)[2]) {
@@ -238,7 +181,7 @@ __device__ __forceinline__ void stg_chunk(float *p, const float (&v)[2]) { *rein
 __device__ __forceinline__ void stg_chunk(float *p, const float (&v)[4]) { *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]); }
 __device__ __forceinline__ void stg_chunk(double *p, const double (&v)[1]) { *p = v[0]; }
 __device__ __forceinline__ void stg_chunk(double *p, const double (&v)[2]) { *reinterpret_cast<double2 *>(p) = make_double2(v[0], v[1]); }
-// predicated stores (see cp_async_p)
+// predicated stores: one PTX predicate instead of a branch around the store (lanes that own only padding rows skip theirs)
 __device__ __forceinline__ void stg_chunk(float *p, const float (&v)[1], unsigned pr) {
     asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %2, 0;\n @q st.global.f32 [%0], %1;\n}" ::"l"(p), "f"(v[0]), "r"(pr) : "memory");
 }
@@ -331,7 +274,7 @@ __global__ void __launch_bounds__(gps_max_warps(NI) * 32, 1)
     constexpr int JX = IPW * NX, JU = IPW * NU;  // element distance between the two instances of a group inside a field
     constexpr int CX = Cfg::CX, CU = Cfg::CU, SX = Cfg::SX, SU = Cfg::SU;
     constexpr unsigned ES = (unsigned)sizeof(T);
-    constexpr unsigned PXB = Cfg::PXB, PUB = Cfg::PUB, STAGE = RING::STAGE, IMGF = RING::IMGF, IMGB = RING::IMGB;
+    constexpr unsigned STAGE = RING::STAGE, IMGF = RING::IMGF, IMGB = RING::IMGB;
     constexpr bool EXT = FAM != 0;
     static_assert(Cfg::ok, "lane mapping not available for this shape");
     extern __shared__ __align__(16) unsigned char smem_raw[];

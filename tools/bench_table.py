@@ -18,7 +18,7 @@ for d in gpu:
     print("| config | kernel plan | ms / batch | instances/s | ADMM it/s/GPU | solved | mean it | algorithmic GB/s (frac of HBM peak) | e2e ms (inst/s) | reference CPU inst/s (threads, 1-thread) | GPU/CPU |")
     print("|---|---|---|---|---|---|---|---|---|---|---|")
     cb = d.get("cpu_baseline") or {}
-    rows = [("C2 (headline)", d["config"], d["ms_per_step"], d["value"], d["admm_iters_per_s_per_gpu"], d["solved_fraction"], 100.0, d["roofline"], d["e2e"], cb)]
+    rows = [("C2 (headline)", d.get("plan") or d["config"], d["ms_per_step"], d["value"], d["admm_iters_per_s_per_gpu"], d["solved_fraction"], 100.0, d["roofline"], d["e2e"], cb)]
     for k, v in (d.get("configs") or {}).items():
         rows.append((k, v["plan"], v["ms_per_step"], v["value"], v["admm_iters_per_s_per_gpu"], v["solved_fraction"], v["mean_iters"], v["roofline"], v.get("e2e"),
                      v.get("cpu_reference") or {}))

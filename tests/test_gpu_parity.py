@@ -484,6 +484,8 @@ _P100 = {(4, 2): (4, 32, True), (4, 4): (4, 32, True), (8, 2): (4, 32, True), (8
          (12, 4): (4, 32, True), (4, 8): (8, 16, True), (8, 8): (8, 16, True), (12, 8): (8, 16, True), (16, 2): (8, 16, True),
          (16, 4): (8, 16, True), (16, 8): (8, 16, True)}
 EXPECTED_F32_PLANS = {50: _P50, 100: _P100}
+# fp64: matrix rows re-read per sweep (narrower lane groups) + dual variables in tensor memory, two columns per value
+EXPECTED_F64_PLANS = {50: {(12, 4): (8, 16, True), (4, 2): (4, 32, True), (8, 4): (4, 32, True), (16, 8): (16, 8, True)}}
 
 
 @pytest.mark.parametrize("N", [50, 100])
@@ -517,6 +519,11 @@ def test_launch_plans_long_horizons_vs_oracle(dims, dt, N):
             assert H.bits_equal(g2[key], o2[key]), (dims, N, kernel, "warm", key)
         if kernel == "gpi":
             assert stt["kernel_family"] in (abi.KERNEL_GPI, abi.KERNEL_GPS)
+            exp64 = EXPECTED_F64_PLANS.get(N, {}).get(dims)
+            if dt == np.float64 and exp64 is not None:
+                assert stt["kernel_family"] == abi.KERNEL_GPI
+                got = (stt["lanes_per_instance"], stt["instances_per_cta"], stt["tmem_cols_per_cta"] > 0)
+                assert got == exp64, (dims, N, got, exp64)
             exp = EXPECTED_F32_PLANS[N].get(dims)
             if dt == np.float32 and exp is not None:
                 assert stt["kernel_family"] == abi.KERNEL_GPI

@@ -217,13 +217,20 @@ int resolve_family(const tinympc_b200_solver *s, const Features &ft, int *smem_o
     const int streamed = !gps_ok ? TINYMPC_KERNEL_TPI
                                  : ((!big_batch || (s->dtype == TINYMPC_F64 && gps_two)) ? TINYMPC_KERNEL_GPS : TINYMPC_KERNEL_TPI);
     if (!gpi_ok) return streamed;
-    // on chip (GPI) unless shared + tensor memory hold fewer than 32 instances per SM (long horizons with wide inputs, fp64)
+    // fp32: on chip (GPI) unless shared + tensor memory hold fewer than 32 instances per SM (long horizons with wide inputs)
     // AND the batch is large.  Measured on B200 (B = 131 072, N = 100): at 16 instances/SM the streamed kernels win by 10-35 %
     // for every shape except (16,8), where the thread-per-instance register footprint costs more than the low on-chip
     // occupancy; at >= 32 instances/SM GPI always wins.
     const int plan = s->dim->gpi_instances_per_cta ? s->dim->gpi_instances_per_cta(s->dtype, s->N, s->max_smem_optin) : 0;
-    const int ipc = plan & 0xffff;
-    const bool tpi_heavy = s->nx >= 16 && s->nu >= 8 && s->dtype == TINYMPC_F32;
+    const int ipc = plan & 0xffff, gpi_warps = plan >> 16;
+    if (s->dtype == TINYMPC_F64) {
+        // fp64 (rows re-read per sweep, duals in tensor memory): on chip wins as soon as four warps per SM are resident
+        // ((12,4,50): 29.6 vs 35.9 ms TPI at 16 instances/SM; (16,8,50): 57.3 vs 88.4 ms at 8/SM), and loses badly with one
+        // warp per SM ((6,3,100): 83 vs 28.4 ms on the streamed lane groups)
+        if (gpi_warps > 0 && gpi_warps < 4 && big_batch) return streamed;
+        return TINYMPC_KERNEL_GPI;
+    }
+    const bool tpi_heavy = s->nx >= 16 && s->nu >= 8;
     if (ipc > 0 && ipc < 32 && !tpi_heavy && big_batch) return streamed;
     return TINYMPC_KERNEL_GPI;
 }

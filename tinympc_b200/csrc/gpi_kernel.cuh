@@ -44,17 +44,31 @@ struct GpiCfg {
     __host__ __device__ static constexpr size_t warp_elems(int N) {
         return (size_t)N * 32 * PVP * 2 + (size_t)(N - 1) * RU * 32 + GBUF1;  // shared memory is the constraint here: one gather buffer
     }
-    // TMEM variant (fp32): the dual pack and d live in tensor memory, CPK 32-bit columns per knot point in the
-    // lane of the owning thread; shared memory keeps the primal pack and the gather scratch
-    static constexpr int CPK = PVP + RU;
+    // per-sweep register needs (elements): backward AmBKt / B^T rows, Kinf^T, Quu_inv, APf, BPf, Qd, Rd; forward A / Kinf rows, B, f
+    static constexpr int BWD_REGS = (RX + RU) * NX + RX * NU + RU * NU + 2 * RX + 2 * RU;
+    static constexpr int FWD_REGS = (RX + RU) * NX + RX * NU + RX;
+    static constexpr int SWEEP_REGS = BWD_REGS > FWD_REGS ? BWD_REGS : FWD_REGS;
+    // TMEM variant: the dual pack and d live in tensor memory, CPK 32-bit columns per knot point (two per fp64 value) in
+    // the lane of the owning thread; shared memory keeps the primal pack and the gather scratch
+    static constexpr int CW = ES / 4;  // 32-bit columns per value
+    static constexpr int CPK = (PVP + RU) * CW;
     __host__ __device__ static constexpr size_t warp_elems_tm(int N) { return (size_t)N * 32 * PVP + GBUF; }
     __host__ __device__ static constexpr int tm_cols(int N) { return N * CPK; }
 };
 
+// fp64: only the rows of the RUNNING sweep are in registers (re-read from the staged blob in shared memory - or from the
+// instance's own blob in a heterogeneous batch - at every sweep start), which halves the register footprint of the matrices
+// and lets fp64 problems use narrower lane groups (nx = 12: L = 8 instead of 16, twice the instances per warp)
+template <typename T>
+__host__ __device__ constexpr bool gpi_per_sweep_rows() {
+    return sizeof(T) == 8;
+}
 template <typename T, int NX, int NU, int L>
-constexpr bool gpi_feasible() {
+__host__ __device__ constexpr bool gpi_feasible() {
     // keep the matrix rows + working set under the 255-register ceiling
-    return GpiCfg<NX, NU, L, (int)sizeof(T)>::MAT_REGS * (int)(sizeof(T) / 4) <= 150;
+    using Cfg = GpiCfg<NX, NU, L, (int)sizeof(T)>;
+    if (gpi_per_sweep_rows<T>()) return Cfg::SWEEP_REGS * 2 <= 112;
+    return Cfg::MAT_REGS * (int)(sizeof(T) / 4) <= 150;
 }
 
 template <typename T, int L>
@@ -121,12 +135,30 @@ __device__ __forceinline__ void tm_wait_ld() { asm volatile("tcgen05.wait::ld.sy
 __device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // makes every later use of v depend on an asm statement that is ordered after tm_wait_ld()
 __device__ __forceinline__ void tm_tie(float &v) { asm volatile("" : "+f"(v)); }
-// double overloads exist only so that the fp64 instantiations (never TMEM) parse
-__device__ __forceinline__ void tm_tie(double &) {}
-template <int n>
-__device__ __forceinline__ void tm_ld(unsigned, double (&)[n]) {}
-template <int n>
-__device__ __forceinline__ void tm_st(unsigned, const double (&)[n]) {}
+// fp64 values occupy two consecutive 32-bit columns (low word first)
+__device__ __forceinline__ void tm_tie(double &v) { asm volatile("" : "+d"(v)); }
+__device__ __forceinline__ void tm_ld(unsigned ta, double (&v)[1]) {
+    unsigned lo, hi;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(ta));
+    asm volatile("mov.b64 %0, {%1,%2};" : "=d"(v[0]) : "r"(lo), "r"(hi));
+}
+__device__ __forceinline__ void tm_ld(unsigned ta, double (&v)[2]) {
+    unsigned w0, w1, w2, w3;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(ta));
+    asm volatile("mov.b64 %0, {%1,%2};" : "=d"(v[0]) : "r"(w0), "r"(w1));
+    asm volatile("mov.b64 %0, {%1,%2};" : "=d"(v[1]) : "r"(w2), "r"(w3));
+}
+__device__ __forceinline__ void tm_st(unsigned ta, const double (&v)[1]) {
+    unsigned lo, hi;
+    asm volatile("mov.b64 {%0,%1}, %2;" : "=r"(lo), "=r"(hi) : "d"(v[0]));
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(ta), "r"(lo), "r"(hi) : "memory");
+}
+__device__ __forceinline__ void tm_st(unsigned ta, const double (&v)[2]) {
+    unsigned w0, w1, w2, w3;
+    asm volatile("mov.b64 {%0,%1}, %2;" : "=r"(w0), "=r"(w1) : "d"(v[0]));
+    asm volatile("mov.b64 {%0,%1}, %2;" : "=r"(w2), "=r"(w3) : "d"(v[1]));
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(ta), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
+}
 
 template <bool B>
 struct BoolTag {
@@ -164,7 +196,8 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
     using Cfg = GpiCfg<NX, NU, L, (int)sizeof(T)>;
     constexpr int RX = Cfg::RX, RU = Cfg::RU, IPW = Cfg::IPW, W = Cfg::W, PVP = Cfg::PVP, NPV = Cfg::NPV;
     constexpr int NXP = Cfg::NXP, NUP = Cfg::NUP, CPK = Cfg::CPK;
-    static_assert(!TM || sizeof(T) == 4, "the TMEM variant is fp32 only");
+    constexpr int CW = Cfg::CW;        // 32-bit tensor-memory columns per value
+    constexpr bool PS = gpi_per_sweep_rows<T>();  // matrix rows re-read at every sweep start (fp64)
     constexpr bool EXACT = (RX * L == NX) && (RU * L == NU);  // no padding rows: predicates vanish
     constexpr unsigned ES = (unsigned)sizeof(T);
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -223,8 +256,49 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
     for (int a = 0; a < RX; ++a) xv[a] = EXACT || (l * RX + a < NX);
 #pragma unroll
     for (int b = 0; b < RU; ++b) uv[b] = EXACT || (l * RU + b < NU);
-    // `src` = a cache blob in the layout above (the staged shared-memory copy, or one instance's blob in global memory)
-    auto load_rows = [&](const T *src) {
+    // `src` = a cache blob in the layout above (the staged shared-memory copy, or one instance's blob in global memory).
+    // Backward-sweep rows (AmBKt, B^T, Kinf^T, Quu_inv, APf, BPf and the cost weights Qd, Rd) and forward-sweep rows (A, Kinf,
+    // B, f) load separately: fp64 re-reads the rows of a sweep when it starts (PS), everything else loads both once.
+    auto load_bwd_rows = [&](const T *src) {
+#pragma unroll
+        for (int a = 0; a < RX; ++a) {
+            const int ii = xv[a] ? l * RX + a : 0;
+#pragma unroll
+            for (int m = 0; m < NX; ++m) mS1b[a][m] = xv[a] ? src[OFF_AMBKT + ii + NX * m] : T(0);
+#pragma unroll
+            for (int j = 0; j < NU; ++j) mKt[a][j] = xv[a] ? src[OFF_K + j + NU * ii] : T(0);  // Kinf^T(i,j) = Kinf(j,i)
+            vQd[a] = xv[a] ? src[OFF_QD + ii] : T(0);
+            vAPf[a] = xv[a] ? src[OFF_APF + ii] : T(0);
+        }
+#pragma unroll
+        for (int b = 0; b < RU; ++b) {
+            const int jj = uv[b] ? l * RU + b : 0;
+#pragma unroll
+            for (int m = 0; m < NX; ++m) mS1b[RX + b][m] = uv[b] ? src[OFF_B + m + NX * jj] : T(0);  // B^T(j,m) = B(m,j)
+#pragma unroll
+            for (int m = 0; m < NU; ++m) mQuu[b][m] = uv[b] ? src[OFF_QUU + jj + NU * m] : T(0);
+            vRd[b] = uv[b] ? src[OFF_RD + jj] : T(0);
+            vBPf[b] = uv[b] ? src[OFF_BPF + jj] : T(0);
+        }
+    };
+    auto load_fwd_rows = [&](const T *src) {
+#pragma unroll
+        for (int a = 0; a < RX; ++a) {
+            const int ii = xv[a] ? l * RX + a : 0;
+#pragma unroll
+            for (int m = 0; m < NX; ++m) mS1f[a][m] = xv[a] ? src[OFF_A + ii + NX * m] : T(0);
+#pragma unroll
+            for (int j = 0; j < NU; ++j) mB[a][j] = xv[a] ? src[OFF_B + ii + NX * j] : T(0);
+            vf[a] = xv[a] ? src[OFF_F + ii] : T(0);
+        }
+#pragma unroll
+        for (int b = 0; b < RU; ++b) {
+            const int jj = uv[b] ? l * RU + b : 0;
+#pragma unroll
+            for (int m = 0; m < NX; ++m) mS1f[RX + b][m] = uv[b] ? src[OFF_K + jj + NU * m] : T(0);
+        }
+    };
+    auto load_rows = [&](const T *src) {  // both sets at once (everything but fp64), in the order of the blob
 #pragma unroll
         for (int a = 0; a < RX; ++a) {
             const int ii = xv[a] ? l * RX + a : 0;
@@ -256,7 +330,9 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
             vBPf[b] = uv[b] ? src[OFF_BPF + jj] : T(0);
         }
     };
-    load_rows(stage);
+    // where this lane's rows come from at a sweep start (PS): the staged blob, or its slot's own blob (heterogeneous batch)
+    const T *rowsrc = stage;
+    if constexpr (!PS) load_rows(stage);
     // TMEM variant: warp 0 allocates all 512 columns (one CTA per SM); warps w and w+4 share a lane quarter and
     // take the column ranges [0, N*CPK) and [N*CPK, 2*N*CPK)
     unsigned tbase = 0;
@@ -281,7 +357,9 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
     //   GB[...]          : gather scratch (one vector of one instance per row)
     //   TMEM variant: PB and D live in tensor memory instead, columns [k*CPK, +PVP) and [k*CPK+PVP, +RU) of the thread's lane
     const int warp_elems = TM ? (int)Cfg::warp_elems_tm(N) : (int)Cfg::warp_elems(N);
-    T *wbase = reinterpret_cast<T *>(smem_raw) + (size_t)warp * warp_elems;
+    // fp64 (PS): the staged blob stays in shared memory for the whole kernel, the state regions start behind it
+    constexpr size_t BLOB_KEEP = PS ? (size_t)BLOB_BYTES : 0;
+    T *wbase = reinterpret_cast<T *>(smem_raw + BLOB_KEEP) + (size_t)warp * warp_elems;
     T *gPA = wbase, *gPB = gPA + N * 32 * PVP, *gD = gPB + N * 32 * PVP, *gGB = TM ? gPA + N * 32 * PVP : gD + (N - 1) * RU * 32;
     const unsigned aPA = (unsigned)__cvta_generic_to_shared(gPA) + (unsigned)(lane * PVP) * ES;
     const unsigned aPB = (unsigned)__cvta_generic_to_shared(gPB) + (unsigned)(lane * PVP) * ES;
@@ -313,7 +391,7 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
 #pragma unroll
             for (int c = 0; c < NPV; ++c) {
                 T t[W];
-                tm_ld(tbase + (unsigned)(k * CPK + c * W), t);
+                tm_ld(tbase + (unsigned)(k * CPK + c * W * CW), t);
 #pragma unroll
                 for (int e = 0; e < W; ++e) v[c * W + e] = t[e];
             }
@@ -335,7 +413,7 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
                 T t[W];
 #pragma unroll
                 for (int e = 0; e < W; ++e) t[e] = v[c * W + e];
-                tm_st(tbase + (unsigned)(k * CPK + c * W), t);
+                tm_st(tbase + (unsigned)(k * CPK + c * W * CW), t);
             }
         } else {
             store_pack(aPB, k, v);
@@ -346,7 +424,7 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
 #pragma unroll
             for (int b = 0; b < RU; ++b) {
                 T t[1];
-                tm_ld(tbase + (unsigned)(k * CPK + PVP + b), t);
+                tm_ld(tbase + (unsigned)(k * CPK + (PVP + b) * CW), t);
                 d[b] = t[0];
             }
         } else {
@@ -366,7 +444,7 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
 #pragma unroll
             for (int b = 0; b < RU; ++b) {
                 T t[1] = {d[b]};
-                tm_st(tbase + (unsigned)(k * CPK + PVP + b), t);
+                tm_st(tbase + (unsigned)(k * CPK + (PVP + b) * CW), t);
             }
         } else {
 #pragma unroll
@@ -491,6 +569,7 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
     // warm start (work->v / work->z come from the caller) or work->v / work->z are being persisted.
     auto forward = [&](auto tag, const bool vin, T &rpx, T &rdx, T &rpu, T &rdu) {
         constexpr bool SLOW = decltype(tag)::value;
+        if constexpr (PS) load_fwd_rows(rowsrc);
         T xo[RX], Xf[NX];
 #pragma unroll
         for (int a = 0; a < RX; ++a) xo[a] = x0o[a];
@@ -845,7 +924,8 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
             const T *pinf = P.Pinf_g;
             if constexpr (HET) {
                 const T *mb = P.models + ib * (int64_t)(BLOB + 1);
-                load_rows(mb);
+                if constexpr (PS) rowsrc = mb;
+                else load_rows(mb);
                 rho_m = mb[BLOB];
                 pinf = mb + OFF_PINF;
             }
@@ -931,6 +1011,9 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
             }
         }
         // work->u.col(0): one rollout step from d_0 (every lane computes, the lanes of slot s store)
+        if constexpr (PS) {
+            if (P.u0 || P.s_x || P.s_u) load_fwd_rows(rowsrc);
+        }
         if (P.u0) {
             __syncwarp();
             T xo0[RX], Xf0[NX], t10[RX + RU];
@@ -1033,6 +1116,7 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
         // shared-memory gathers).
         do {
         // ---- terminal cost + backward pass (update_linear_cost fused, software-pipelined by one column) ----
+        if constexpr (PS) load_bwd_rows(rowsrc);
         T po[RX], Pf[NX];
         {
             T pa[PVP], pb[PVP];
@@ -1127,7 +1211,7 @@ __global__ void __launch_bounds__(GPI_MAX_WARPS * 32, 1)
 struct GpiPlan {
     int L = 0, warps = 0;
     size_t smem = 0;
-    bool tm = false;  // dual packs + d in tensor memory (fp32)
+    bool tm = false;  // dual packs + d in tensor memory
 };
 
 // TINYMPC_GPI_TMEM=0 keeps everything in shared memory (A/B switch for measurements)
@@ -1138,12 +1222,15 @@ inline bool gpi_allow_tm() {
 
 template <typename T, int NX, int NU, int L, bool TM>
 inline void gpi_consider(int N, int max_smem, GpiPlan &best) {
-    if constexpr (gpi_feasible<T, NX, NU, L>() && (!TM || sizeof(T) == 4)) {
+    if constexpr (gpi_feasible<T, NX, NU, L>()) {
         using Cfg = GpiCfg<NX, NU, L, (int)sizeof(T)>;
         const size_t per_warp = (TM ? Cfg::warp_elems_tm(N) : Cfg::warp_elems(N)) * sizeof(T);
-        // the TMA staging area aliases the start of the state region: the allocation is at least as large as the blob
+        // fp32: the TMA staging area aliases the start of the state region (the allocation is at least as large as the blob);
+        // fp64: the blob stays resident in front of the state regions (matrix rows are re-read at every sweep start)
         const size_t blob = ((size_t)(3 * NX * NX + 2 * NX * NU + NU * NU + 4 * NX + 2 * NU) * sizeof(T) + 15) / 16 * 16 + 64;
-        int w = (int)std::min<size_t>(GPI_MAX_WARPS, (size_t)max_smem / per_warp);
+        const size_t keep = gpi_per_sweep_rows<T>() ? ((size_t)(3 * NX * NX + 2 * NX * NU + NU * NU + 4 * NX + 2 * NU) * sizeof(T) + 15) / 16 * 16 : 0;
+        if ((size_t)max_smem < keep + per_warp) return;
+        int w = (int)std::min<size_t>(GPI_MAX_WARPS, ((size_t)max_smem - keep) / per_warp);
         if (TM) {
             // every TMEM lane quarter is shared by the warps w, w+4, ...: 512 columns / (N*CPK columns per warp)
             const int cols = Cfg::tm_cols(N);
@@ -1157,7 +1244,7 @@ inline void gpi_consider(int N, int max_smem, GpiPlan &best) {
         if (better) {
             best.L = L;
             best.warps = w;
-            best.smem = std::max(per_warp * (size_t)w, blob);
+            best.smem = std::max(keep + per_warp * (size_t)w, blob);
             best.tm = TM;
         }
     }
@@ -1192,7 +1279,7 @@ inline int gpi_fit_T(int N, int max_smem) {
 
 template <typename T, int NX, int NU, int L, bool FAST, bool HET, bool TM, bool MM = false>
 int launch_gpi_L(LaunchDesc *d, const GpiPlan &plan, const KParams<T, NX, NU> &P, const T *gmat) {
-    if constexpr (gpi_feasible<T, NX, NU, L>() && (!TM || sizeof(T) == 4)) {
+    if constexpr (gpi_feasible<T, NX, NU, L>()) {
         auto kern = gpi_solve_kernel<T, NX, NU, L, FAST, HET, TM, MM>;
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem) != cudaSuccess)
             return TINYMPC_ERR_CUDA;

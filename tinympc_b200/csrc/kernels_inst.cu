@@ -119,9 +119,8 @@ int launch_gpi(LaunchDesc *d) {
 #ifdef TM_GPI_L16
     TM_GPI_L(16)
 #else
-    if constexpr (sizeof(T) == 8) {  // fp64 needs L = 16 from nx = 12 on (see gpi_plan)
-        TM_GPI_CASE(16, false, false)
-        TM_GPI_CASE(16, true, false)
+    if constexpr (sizeof(T) == 8) {  // fp64 may need L = 16 for the widest states (see gpi_plan)
+        TM_GPI_L(16)
     }
 #endif
 #undef TM_GPI_L

@@ -18,6 +18,7 @@ from tinympc_b200.solver import BatchedTinySolver, setup_problem  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--B", type=int, default=131072)
 ap.add_argument("--reps", type=int, default=2)
+ap.add_argument("--only", default="", help="f64_12_4: just the fp64 (12,4,50) big-batch row on the on-chip kernel (ncu capture)")
 a = ap.parse_args()
 FAM = {"gpi": abi.KERNEL_GPI, "gps": abi.KERNEL_GPS, "tpi": abi.KERNEL_TPI, "auto": abi.KERNEL_AUTO}
 NAMES = {1: "tpi", 2: "gpi", 4: "gps"}
@@ -26,6 +27,8 @@ shapes = [(np.float32, 4, 8, 100), (np.float32, 8, 8, 100), (np.float32, 12, 4, 
           (np.float64, 12, 4, 50), (np.float64, 6, 3, 100), (np.float64, 4, 2, 50), (np.float64, 16, 8, 50),
           # small batches (one thread per instance cannot fill the GPU)
           (np.float64, 12, 4, 50, 4096), (np.float32, 12, 8, 100, 4096), (np.float32, 16, 4, 100, 8192), (np.float64, 8, 4, 50, 16384)]
+if a.only == "f64_12_4":
+    shapes = [(np.float64, 12, 4, 50)]
 print("| dtype | nx | nu | N | B | family asked | ran | plan | ms | ADMM it/s |")
 print("|---|---|---|---|---|---|---|---|---|---|")
 for shp in shapes:
@@ -37,7 +40,7 @@ for shp in shapes:
     spec.settings.max_iter = 50
     prob = setup_problem(spec, dt)
     inst = wl.random_instances(B, nx, N, seed=2, dtype=dt)
-    for fam in ("auto", "gpi", "gps", "tpi"):
+    for fam in (("gpi",) if a.only else ("auto", "gpi", "gps", "tpi")):
         try:
             s = BatchedTinySolver(prob, spec.settings, device=0, kernel=FAM[fam])
             batch, out = s.make_device_batch(inst["x0"], inst["Xref"], None, cold_start=True)

@@ -10,9 +10,11 @@
 //     a small shared-memory buffer (STS + 16-byte broadcast LDS);
 //   * the N-indexed state lives on chip for the whole solve: the primal pack (vnew rows, znew rows) as one
 //     16-byte vector per lane and knot point in shared memory; the dual pack (g rows, y rows) and d either next
-//     to it in shared memory, or (TM = true, fp32) in TENSOR MEMORY — 5 of the thread's own 32-bit TMEM columns
-//     per knot point, tcgen05.ld/st.32x32b — which halves the shared-memory footprint and doubles the instances
+//     to it in shared memory, or (TM = true) in TENSOR MEMORY — the thread's own 32-bit TMEM columns, 5 per knot point in
+//     fp32 (two per fp64 value), tcgen05.ld/st.32x32b — which halves the shared-memory footprint and doubles the instances
 //     (= warps) resident per SM; only the final trajectories / residuals are written back;
+//   * fp64: only the rows of the running sweep are in registers (re-read from the resident blob at every sweep start), so
+//     that narrower lane groups fit (gpi_per_sweep_rows);
 //   * the kernel is persistent: one CTA per SM; every lane group ("slot") pulls its next instance from a
 //     global atomic counter as soon as its current one terminates (per-instance termination, admm.cpp:310-328).
 // Reference semantics: tiny_solve -> solve (admm.cpp:331-455); per-iteration order as in SURVEY A.2.

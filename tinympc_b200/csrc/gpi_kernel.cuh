@@ -18,7 +18,7 @@
 //   * the kernel is persistent: one CTA per SM; every lane group ("slot") pulls its next instance from a
 //     global atomic counter as soon as its current one terminates (per-instance termination, admm.cpp:310-328).
 // Reference semantics: tiny_solve -> solve (admm.cpp:331-455); per-iteration order as in SURVEY A.2.
-// Scope: box constraints (admm.cpp:85-98).  Cones / hyperplanes run on the TPI kernel.
+// Scope: box constraints (admm.cpp:85-98).  Cones / hyperplanes run on the streamed lane-group kernel (gps_kernel.cuh).
 #pragma once
 #include <cuda/barrier>
 

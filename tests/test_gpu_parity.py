@@ -638,3 +638,33 @@ def test_bounds_with_signed_zeros(kernel):
         assert H.bits_equal(g[key], o[key]), (kernel, key)
     z = o["znew"]
     assert (z == 0).any() and np.signbit(z[z == 0]).any() and (~np.signbit(z[z == 0])).any()  # both zero signs occur
+
+
+def test_device_resident_closed_loop_with_cones_matches_oracle():
+    """The device-resident MPC loop on the conic path (rocket landing, fp64, streamed lane groups): slacks and duals of the box
+    AND cone constraints stay in HBM between steps (examples/rocket_landing_mpc.cpp:118-136 pattern: warm start, x0 advanced
+    with the rollout input); every step equals the oracle stepping the same loop on the host."""
+    from tinympc_b200.closed_loop import DeviceMPCLoop
+
+    spec = wl.rocket(N=20)
+    dt = np.float64
+    prob = setup_problem(spec, dt)
+    st = abi.Settings.from_buffer_copy(spec.settings)
+    st.max_iter = 40
+    B, steps = 90, 4
+    inst = wl.rocket_instances(B, N=20, seed=4, dtype=dt)
+    # cone slacks are re-initialised from the previous rollout at the start of solve() (admm.cpp:352-376): work->x / work->u
+    # belong to the warm-start state of the conic path, next to the cone slack / dual pairs
+    soc = ("x", "u", "vcnew", "zcnew", "gc", "yc")
+    solver = _mk_solver(prob, st, "auto")
+    loop = DeviceMPCLoop(solver, inst["x0"], reset_duals=False, extra_state=soc)
+    x0, state = inst["x0"].copy(), None
+    for k in range(steps):
+        out = loop.step(inst["Xref"], inst["Uref"])
+        assert solver.stats()["kernel_family"] == abi.KERNEL_GPS
+        o = _port(prob, st, x0, inst["Xref"], inst["Uref"], state, state is None, tuple(H.SOC_STATE))
+        for key in H.OUT_KEYS + list(loop.fields):
+            assert H.bits_equal(out[key].cpu().numpy(), o[key]), (k, key)
+        assert H.bits_equal(out["u0"].cpu().numpy(), np.ascontiguousarray(o["u"][:, 0, :])), (k, "u0")
+        state = {n: o[n] for n in H.SOC_STATE}
+        x0 = loop.x0.cpu().numpy().copy()

@@ -18,6 +18,8 @@ from .solver import BatchedTinySolver
 
 # box-constrained warm start: slacks + duals (+ the previous-iteration slacks v, z, which only feed the dual residual of
 # the next solve's first iteration; drop them with exact_first_residual=False for ~30 % more steps per second)
+# Cones / hyperplanes: pass extra_state=("x", "u", <the family's slack / dual fields>), e.g. ("x", "u", "vcnew", "zcnew", "gc", "yc") —
+# solve() re-initialises those slacks from the previous rollout work->x / work->u (admm.cpp:352-376).
 WARM_FIELDS = ("v", "z", "vnew", "znew", "g", "y")
 WARM_FIELDS_FAST = ("vnew", "znew", "g", "y")
 

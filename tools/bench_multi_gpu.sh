@@ -1,4 +1,4 @@
-# multi-GPU bench (the driver's launch line):  gpurun --gpus N -- bash tools/gpu_r02_n.sh N
+# multi-GPU bench (the driver's launch line):  gpurun --gpus N -- bash tools/bench_multi_gpu.sh N
 cd $GRAFT_REPO_ROOT
 N=${1:-2}
 mkdir -p gpurun_out

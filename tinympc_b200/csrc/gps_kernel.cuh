@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(gps_max_warps(NI) * 32, 1)
         }
     };
 
-    // ---- shared memory of this warp: gather scratch (state vectors | input vectors) + cp.async ring (S stages) ----
+    // ---- shared memory of this warp: gather scratch (state vectors | input vectors) + parked rows + ring of record images + mbarriers ----
     constexpr unsigned wbytes = (unsigned)RING::WARP_BYTES;
     const unsigned aZero = aBlob + BLOB_BYTES;  // IMGF bytes of zeros (per CTA)
     const unsigned aGX = aZero + (unsigned)RING::ZERO_BYTES + (unsigned)warp * wbytes;
@@ -579,8 +579,7 @@ __global__ void __launch_bounds__(gps_max_warps(NI) * 32, 1)
         }
     };
 
-    // ---- ring producers: all copies of one sweep step form one cp.async group.  cx / cu = this lane's rows in the record
-    // of knot point k (first instance of the group), xr / ur = its reference columns; sb = byte offset of the stage ----
+    // ---- ring producers: one bulk copy per sweep step (record block of knot point k -> stage image) ----
     // forward step k into stage si: the record block of knot point k (one bulk copy); this lane's reference columns of
     // that step are pulled into L2 (per-instance references come from HBM)
     auto issue_fwd = [&](int k, int si, const T *(&xr)[NI], const T *(&ur)[NI]) {

@@ -668,3 +668,36 @@ def test_device_resident_closed_loop_with_cones_matches_oracle():
         assert H.bits_equal(out["u0"].cpu().numpy(), np.ascontiguousarray(o["u"][:, 0, :])), (k, "u0")
         state = {n: o[n] for n in H.SOC_STATE}
         x0 = loop.x0.cpu().numpy().copy()
+
+
+def test_auto_rule_choices():
+    """TINYMPC_KERNEL_AUTO follows the measured rules of DESIGN.md §5 (csrc/capi.cu: resolve_family): which family serves
+    which (constraints, dtype, shape, batch size).  Two iterations per instance are enough to see the choice in stats()."""
+    import torch
+
+    big = 148 * 384 + 64  # "big batch": one thread per instance fills the GPU
+    cases = [
+        ("box fp32, fits 64/SM on chip", wl.random_lti(12, 4, 50, seed=1), np.float32, 64, abi.KERNEL_GPI),
+        ("box fp32, 16/SM on chip, big batch -> thread per instance", wl.random_lti(4, 8, 100, seed=1), np.float32, big, abi.KERNEL_TPI),
+        ("box fp32, 16/SM on chip, small batch -> on chip", wl.random_lti(4, 8, 100, seed=1), np.float32, 4096, abi.KERNEL_GPI),
+        ("box fp32 (16,8,100): on chip even at 16/SM", wl.random_lti(16, 8, 100, seed=1), np.float32, big, abi.KERNEL_GPI),
+        ("box fp64, four warps per SM on chip", wl.random_lti(12, 4, 50, seed=1), np.float64, big, abi.KERNEL_GPI),
+        ("box fp64, one warp per SM on chip, small shape -> streamed lane groups", wl.random_lti(6, 3, 100, seed=1), np.float64, big, abi.KERNEL_GPS),
+        ("cones -> streamed lane groups", wl.rocket(N=20), np.float64, 256, abi.KERNEL_GPS),
+    ]
+    for what, spec, dt, B, expect in cases:
+        st = abi.Settings.from_buffer_copy(spec.settings)
+        st.max_iter = 2
+        prob = setup_problem(spec, dt)
+        solver = _mk_solver(prob, st, "auto")
+        x0 = np.zeros((B, spec.nx), dt)
+        x0[:, 0] = np.linspace(-1, 1, B)
+        Xref = np.zeros((spec.N, spec.nx), dt)
+        batch, out = solver.make_device_batch(x0, Xref, None, cold_start=True)
+        solver.solve_device(batch)
+        torch.cuda.synchronize()
+        assert solver.stats()["kernel_family"] == expect, (what, solver.stats()["kernel_family"])
+        assert int(out["iter"].min().item()) >= 1
+        solver.close()
+        del batch, out
+        torch.cuda.empty_cache()

@@ -30,9 +30,9 @@ if a.config == "c2":
 elif a.config == "c3":
     spec, dt, B = wl.quadrotor(N=50), np.float32, a.B or 65536
     inst = wl.tracking_instances(B, N=50, seed=0, dtype=dt)
-elif a.config == "c4":
+elif a.config in ("c4", "c4p"):  # c4p: one reference trajectory per instance (what bench.py's C4 entry runs)
     spec, dt, B = wl.rocket(N=100), np.float64, a.B or 16384
-    inst = wl.rocket_instances(B, N=100, seed=0, dtype=dt)
+    inst = wl.rocket_instances(B, N=100, seed=0, dtype=dt, per_instance_refs=a.config == "c4p")
 else:
     raise SystemExit("config")
 if a.max_iter:

@@ -14,6 +14,8 @@ $T ncu --set full --clock-control none --import-source on -k regex:gpi_solve -s 
     python tools/quick_bench.py --kernel gpi --config c2 --mode strict --reps 3 > gpurun_out/r02_ncu_gpi_c2.log 2>&1
 $T ncu --set full --clock-control none --import-source on -k regex:gps_solve -s 3 -c 1 -f -o gpurun_out/r02_gps_c4 \
     python tools/quick_bench.py --kernel gps --config c4 --mode strict --reps 3 > gpurun_out/r02_ncu_gps_c4.log 2>&1
+$T ncu --set full --clock-control none --import-source on -k regex:gps_solve -s 3 -c 1 -f -o gpurun_out/r02_gps_c4p \
+    python tools/quick_bench.py --kernel gps --config c4p --mode strict --reps 3 > gpurun_out/r02_ncu_gps_c4p.log 2>&1
 $T ncu --set full --clock-control none --import-source on -k regex:gpi_solve -s 3 -c 1 -f -o gpurun_out/r02_gpi_c3 \
     python tools/quick_bench.py --kernel gpi --config c3 --mode strict --reps 3 > gpurun_out/r02_ncu_gpi_c3.log 2>&1
 $T python tools/roofline_sweep.py > gpurun_out/r02_sweep_1gpu.md 2> gpurun_out/r02_sweep.err

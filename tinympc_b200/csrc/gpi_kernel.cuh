@@ -1263,13 +1263,18 @@ inline GpiPlan gpi_plan(int N, int max_smem) {
                          || true
 #endif
         ;
-    gpi_consider<T, NX, NU, 4, false>(N, max_smem, p);
-    gpi_consider<T, NX, NU, 8, false>(N, max_smem, p);
-    if constexpr (L16) gpi_consider<T, NX, NU, 16, false>(N, max_smem, p);
+    // TINYMPC_GPI_LANES=4|8|16 restricts the choice to one group width (A/B switch for measurements)
+    const char *e = std::getenv("TINYMPC_GPI_LANES");
+    const int only = e ? std::atoi(e) : 0;
+    if (!only || only == 4) gpi_consider<T, NX, NU, 4, false>(N, max_smem, p);
+    if (!only || only == 8) gpi_consider<T, NX, NU, 8, false>(N, max_smem, p);
+    if constexpr (L16)
+        if (!only || only == 16) gpi_consider<T, NX, NU, 16, false>(N, max_smem, p);
     if (gpi_allow_tm()) {  // taken only when it holds more instances per SM
-        gpi_consider<T, NX, NU, 4, true>(N, max_smem, p);
-        gpi_consider<T, NX, NU, 8, true>(N, max_smem, p);
-        if constexpr (L16) gpi_consider<T, NX, NU, 16, true>(N, max_smem, p);
+        if (!only || only == 4) gpi_consider<T, NX, NU, 4, true>(N, max_smem, p);
+        if (!only || only == 8) gpi_consider<T, NX, NU, 8, true>(N, max_smem, p);
+        if constexpr (L16)
+            if (!only || only == 16) gpi_consider<T, NX, NU, 16, true>(N, max_smem, p);
     }
     return p;
 }

@@ -15,13 +15,19 @@ from tinympc_b200.solver import BatchedTinySolver, setup_problem  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--only", default="", help="c2 | c4")
+ap.add_argument("--max-b", type=int, default=1 << 30)
 a = ap.parse_args()
 NAMES = {1: "tpi", 2: "gpi", 4: "gps"}
 print("| config | B | family | plan | ms per solve | instances/s | ADMM it/s | us per instance-iteration |")
 print("|---|---|---|---|---|---|---|---|")
 for cfg, sizes in (("C2 quadrotor hovering fp32 N=50, 100 it", [1, 64, 1024, 4096, 16384, 65536, 262144, 1048576]),
                    ("C4 rocket + cones fp64 N=100, 100 it", [1, 64, 1024, 4096, 16384, 65536, 131072])):
+    if a.only and not cfg.lower().startswith(a.only):
+        continue
     for B in sizes:
+        if B > a.max_b:
+            continue
         if cfg.startswith("C2"):
             spec, dt = wl.quadrotor(N=50), np.float32
             inst = wl.hovering_instances(B, N=50, dtype=dt)
